@@ -1,0 +1,118 @@
+/* lookonce_b200.h -- C ABI of the B200-native LookOnceToHear inference engine.
+ *
+ * Drop-in boundary for ONE path of vb000/LookOnceToHear: the inference forward of its two
+ * networks.  The reference is pure Python; the interface each entry point stands in for is the
+ * Python method the reference's evaluation path calls (all paths relative to /root/reference):
+ *
+ *   l2h_sep_create / l2h_sep_load_weight / l2h_sep_commit_weights
+ *        <- Net.__init__ + load_state_dict      src/models/tfgridnet_realtime/net.py:20-49,
+ *                                               src/ts_hear_test.py:18-34 (load_model)
+ *   l2h_sep_state_bytes / l2h_sep_state_init
+ *        <- Net.init_buffers                    net.py:51-52, tfgridnet_causal.py:173-186,408-427
+ *   l2h_sep_forward
+ *        <- Net.predict / Net.forward           net.py:54-76  -> TFGridNet.forward
+ *                                               tfgridnet_causal.py:188-283
+ *   l2h_sep_stream_host
+ *        <- the chunk loop around Net.predict(chunk, embed, state, pad=False)  
+ *           with host buffers: H2D of each chunk and D2H of each result inside the call
+ *   l2h_embed_create / l2h_embed_load_weight / l2h_embed_commit_weights / l2h_embed_forward
+ *        <- EmbedTFGridNet.__init__/forward     src/models/tfgridnet_orig/tfgridnet.py:88-127
+ *
+ * Conventions follow the reference's only FFI (src/datasets/motion_simulator.py:30-95): every
+ * function returns int (0 = OK, non-zero = error, text via l2h_last_error()), handles are opaque
+ * void*, buffers are plain float pointers + sizes, explicit *_destroy.  No torch types.  Device
+ * pointers are CUDA device memory of the current device; `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream).  Nothing synchronises the stream except where stated.
+ * One handle per device; a handle is not thread-safe.
+ */
+#ifndef LOOKONCE_B200_H
+#define LOOKONCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L2H_ABI_VERSION 1
+
+/* configs/tsh.json:5-19 -> Net(**model_params) */
+typedef struct l2h_sep_config {
+    int32_t stft_chunk_size; /* 128 */
+    int32_t stft_pad_size;   /* 64  */
+    int32_t embed_dim;       /* 256 */
+    int32_t num_ch;          /* 2   */
+    int32_t D;               /* 64  */
+    int32_t L;               /* 4 heads */
+    int32_t I;               /* 1   */
+    int32_t J;               /* 1   */
+    int32_t B;               /* number of GridNet blocks (3) */
+    int32_t H;               /* 64  */
+    int32_t local_atten_len; /* 50  */
+    int32_t use_attn;        /* 1   */
+    int32_t lookahead;       /* 1   */
+    int32_t chunk_causal;    /* 1   */
+    int32_t num_src;         /* 2   */
+} l2h_sep_config;
+
+/* flags for l2h_sep_forward */
+#define L2H_FLAG_TAPS 1u /* also copy the activations after every stage into the tap area */
+
+int l2h_abi_version(void);
+const char* l2h_last_error(void);
+
+/* ---- separation network -------------------------------------------------------------------- */
+int l2h_sep_create(const l2h_sep_config* cfg, void** handle);
+int l2h_sep_destroy(void* handle);
+
+/* name = a key of the reference state_dict without the Lightning "model." prefix, e.g.
+ * "tfgridnet.blocks.0.intra_rnn.weight_ih_l0"; data = HOST fp32, contiguous, numel elements.
+ * Repacks into the engine's layouts in a host staging buffer.  Unknown names -> error 2. */
+int l2h_sep_load_weight(void* handle, const char* name, const float* host_data, int64_t numel);
+/* number of reference tensors the engine expects / has received so far */
+int l2h_sep_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loaded);
+/* upload the staged weights (one H2D of ~8 MB on `stream`, then synchronises it) */
+int l2h_sep_commit_weights(void* handle, void* stream);
+
+int l2h_sep_state_bytes(void* handle, int32_t batch, size_t* bytes);
+int l2h_sep_state_init(void* handle, void* state_dev, int32_t batch, void* stream);
+/* floats per stream record and header bytes, for host code that builds views of the state */
+int l2h_sep_state_layout(void* handle, int64_t* header_bytes, int64_t* stream_stride_floats);
+
+int l2h_sep_workspace_bytes(void* handle, int32_t batch, int32_t frames, uint32_t flags, size_t* bytes);
+
+/* One call = `frames` hops of 128 samples for `batch` independent streams.
+ *   x_dev   [batch][num_ch][*]  fp32, strides in floats; samples at index >= x_len read as zero
+ *           (this is where net.py's mod-pad and look-ahead zero padding happen)
+ *   emb_dev [batch][256]
+ *   y_dev   [batch][num_src][*] fp32; samples 0 .. min(y_len, 128*frames)-1 are written
+ * The state is advanced in place.  Asynchronous on `stream`. */
+int l2h_sep_forward(void* handle, const float* x_dev, int64_t x_batch_stride, int64_t x_ch_stride,
+                    int32_t x_len, const float* emb_dev, void* state_dev, float* y_dev,
+                    int64_t y_batch_stride, int64_t y_ch_stride, int32_t y_len, int32_t batch,
+                    int32_t frames, void* workspace_dev, size_t workspace_bytes, uint32_t flags,
+                    void* stream);
+
+/* Streaming with HOST buffers (the end-to-end path): for i in [0, n_chunks):
+ *   H2D x_host[:, :, 128*i*chunks_per_call : ... + 128*chunks_per_call + 64]  (pinned memory),
+ *   forward of chunks_per_call frames, D2H of the 128*chunks_per_call new samples; then one
+ *   stream synchronise at the end.  x_host [batch][num_ch][x_len], y_host [batch][num_src][y_len]. */
+int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const float* emb_dev,
+                        void* state_dev, float* y_host, int32_t y_len, int32_t batch,
+                        int32_t n_calls, int32_t chunks_per_call, float* x_stage_dev,
+                        float* y_stage_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* stream);
+
+/* where the tap area starts inside the workspace (floats) and its stage count; stage s holds
+ * [batch*frames*97*64] floats: 0 = encoder out, then per block: after intra, after inter, block out */
+int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* offset_floats,
+                     int32_t* n_stages);
+
+/* number of kernels one l2h_sep_forward launches (for bench.py's gpu_launches) */
+int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOOKONCE_B200_H */

@@ -1,0 +1,164 @@
+// lstm_rec: the serial part of every LSTM in both networks (hidden size 64).
+//
+// The input projection W_ih x + b_ih + b_hh for all steps is a rows_gemm done beforehand
+// ("gx", gate columns packed as j*4 + q with q in {i,f,g,o}: thread tid of this kernel owns
+// column tid).  What is left is, per step, a 256x64 mat-vec with W_hh, the cell update and
+// one barrier -- a latency chain.  One CTA (256 threads) runs NSEQ independent sequences in
+// lock-step with W_hh row-resident in registers (64 regs/thread) and h broadcast through shared
+// memory; the FMAs are packed FFMA2 along k.
+//
+// Row addressing (rows of gx / out are activation rows of the [B,T,F,C] tensors):
+//   seq -> (o = seq / inner_count, i = seq % inner_count)
+//   row(seq, s) = o*outer_stride + i*inner_stride + s*step_stride
+// intra (along F): inner_count=1, outer_stride=F(+pad), step_stride=1
+// inter (along T): inner_count=F, outer_stride=T*F, inner_stride=1, step_stride=F
+//
+// Reference semantics: torch.nn.LSTM cell, gate order i,f,g,o
+// (tfgridnet_causal.py:336-346, used :512 and :529).
+#pragma once
+#include "common.cuh"
+
+namespace l2h {
+
+struct LstmArgs {
+    const float* gx;       // rows x gx_ld; direction d uses columns [d*256, d*256+256)
+    int64_t gx_ld;
+    float* out;            // rows x out_ld; direction d writes columns [d*64, d*64+64)
+    int64_t out_ld;
+    const float* whh;      // [ndir][256 (j*4+q)][64]
+    float* h_state;        // carried state (read at start, written at end) or null;
+    float* c_state;        //   element (seq, j) at (seq/inner_count)*hc_outer_stride + (seq%inner_count)*64 + j
+    int64_t hc_outer_stride;
+    int nseq, L;
+    int inner_count;
+    int64_t outer_stride, inner_stride, step_stride;
+    int ndir;              // 1 or 2; direction 1 runs the steps in reverse
+};
+
+template <int NSEQ>
+__global__ void __launch_bounds__(256, (NSEQ <= 4 ? 2 : 1))
+lstm_rec_kernel(const LstmArgs a) {
+    __shared__ __align__(16) float hbuf[2][NSEQ][64];
+
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const int seq0 = blockIdx.x * NSEQ;
+    const int j = tid >> 2, q = tid & 3;
+
+    // W_hh row (j*4+q) of this direction -> registers, as 32 k-pairs
+    float2 w[32];
+    {
+        const float4* wp = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + tid) * 64);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 t = __ldg(wp + k);
+            w[2 * k] = make_float2(t.x, t.y);
+            w[2 * k + 1] = make_float2(t.z, t.w);
+        }
+    }
+
+    int64_t base[NSEQ], hc[NSEQ];
+    bool valid[NSEQ];
+    float c[NSEQ];
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) {
+        const int seq = seq0 + s;
+        valid[s] = seq < a.nseq;
+        const int sq = valid[s] ? seq : 0;
+        base[s] = (int64_t)(sq / a.inner_count) * a.outer_stride + (int64_t)(sq % a.inner_count) * a.inner_stride;
+        hc[s] = (int64_t)(sq / a.inner_count) * a.hc_outer_stride + (int64_t)(sq % a.inner_count) * 64 + j;
+        c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
+        if (q == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
+    }
+
+    const int64_t gcol = (int64_t)dir * 256 + tid;
+    auto step_of = [&](int it) { return dir == 0 ? it : a.L - 1 - it; };
+
+    // prefetch gx two steps ahead
+    float g0[NSEQ], g1[NSEQ];
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) {
+        g0[s] = valid[s] ? __ldg(a.gx + (base[s] + (int64_t)step_of(0) * a.step_stride) * a.gx_ld + gcol) : 0.f;
+        g1[s] = (valid[s] && a.L > 1)
+                    ? __ldg(a.gx + (base[s] + (int64_t)step_of(1) * a.step_stride) * a.gx_ld + gcol) : 0.f;
+    }
+    __syncthreads();
+
+    // activation constants: sigmoid for i,f,o ; tanh for g (q == 2):  y = A / (1 + exp(-S x)) + Bc
+    const float S = (q == 2) ? 2.f : 1.f;
+    const float Aa = (q == 2) ? 2.f : 1.f;
+    const float Bc = (q == 2) ? -1.f : 0.f;
+    const int lane = tid & 31;
+    const int qbase = lane & ~3;
+
+    int cur = 0;
+    for (int it = 0; it < a.L; ++it) {
+        const int st = step_of(it);
+        float g2[NSEQ];
+        if (it + 2 < a.L) {
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s)
+                g2[s] = valid[s]
+                            ? __ldg(a.gx + (base[s] + (int64_t)step_of(it + 2) * a.step_stride) * a.gx_ld + gcol)
+                            : 0.f;
+        } else {
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s) g2[s] = 0.f;
+        }
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][s][0]);
+            float2 acc0 = make_float2(g0[s], 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float4 h4 = hp[k];
+                acc0 = ffma2(w[2 * k], make_float2(h4.x, h4.y), acc0);
+                acc1 = ffma2(w[2 * k + 1], make_float2(h4.z, h4.w), acc1);
+            }
+            const float pre = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+            const float act = __fdividef(Aa, 1.f + __expf(-S * pre)) + Bc;
+            const float gi = __shfl_sync(0xffffffffu, act, qbase + 0);
+            const float gf = __shfl_sync(0xffffffffu, act, qbase + 1);
+            const float gg = __shfl_sync(0xffffffffu, act, qbase + 2);
+            const float go = __shfl_sync(0xffffffffu, act, qbase + 3);
+            c[s] = gf * c[s] + gi * gg;
+            const float h = go * fast_tanh(c[s]);
+            if (q == 0) {
+                hbuf[cur ^ 1][s][j] = h;
+                if (valid[s])
+                    a.out[(base[s] + (int64_t)st * a.step_stride) * a.out_ld + dir * 64 + j] = h;
+            }
+            g0[s] = g1[s];
+            g1[s] = g2[s];
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    if (a.h_state != nullptr) {
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            if (valid[s] && q == 0) {
+                a.h_state[hc[s]] = hbuf[cur][s][j];
+                a.c_state[hc[s]] = c[s];
+            }
+        }
+    }
+}
+
+inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st) {
+    if (a.nseq <= 0 || a.L <= 0) return cudaErrorInvalidValue;
+    // smallest NSEQ that still fits one wave of 148 SMs x 2 CTAs
+    const int slots = 296;
+    int nseq_per = 1;
+    while (nseq_per < 4 && ((a.nseq + nseq_per - 1) / nseq_per) * a.ndir > slots) nseq_per *= 2;
+    dim3 grid((a.nseq + nseq_per - 1) / nseq_per, a.ndir);
+    switch (nseq_per) {
+        case 1: lstm_rec_kernel<1><<<grid, 256, 0, st>>>(a); break;
+        case 2: lstm_rec_kernel<2><<<grid, 256, 0, st>>>(a); break;
+        default: lstm_rec_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace l2h

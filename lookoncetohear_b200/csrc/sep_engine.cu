@@ -1,0 +1,468 @@
+// Separation engine: weight packing, state, the per-call kernel chain and the C ABI
+// (include/lookonce_b200.h).  Host side of the hot path = this file; no torch anywhere.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lookonce_b200.h"
+#include "gemm.cuh"
+#include "lstm.cuh"
+#include "sep_kernels.cuh"
+
+namespace l2h {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(3, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+    } while (0)
+
+struct Slot {
+    int64_t off;    // floats into the packed buffer
+    int64_t numel;  // of the reference tensor
+    // repack(src_host, dst_host_base)
+    std::function<void(const float*, float*)> repack;
+    bool loaded = false;
+    bool accumulate = false;   // LSTM biases: b_ih and b_hh of one direction sum into one destination
+    std::vector<float> raw;    // accumulate slots keep their tensor; the sum is formed at commit
+};
+
+struct SepEngine {
+    l2h_sep_config cfg;
+    int n_blocks;
+    std::vector<float> host;        // staging
+    float* dev = nullptr;           // packed weights
+    int64_t total = 0;
+    std::map<std::string, Slot> slots;
+    SepWeights w;
+    std::vector<BlockWeights> bw;
+    bool committed = false;
+};
+
+static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+// gate-row permutation: packed row j*4+q <- reference row q*64+j
+static inline int perm_row(int p) { return (p & 3) * 64 + (p >> 2); }
+
+static void build_layout(SepEngine* e) {
+    int64_t cur = 0;
+    auto alloc = [&](int64_t n) { int64_t o = cur; cur = align4(cur + n); return o; };
+    auto& S = e->slots;
+    auto plain = [&](const std::string& name, int64_t n) {
+        int64_t o = alloc(n);
+        S[name] = Slot{o, n, [o, n](const float* s, float* d) { memcpy(d + o, s, n * sizeof(float)); }};
+        return o;
+    };
+    auto transposed = [&](const std::string& name, int rows, int cols, int ld_out) {
+        // reference [rows][cols] -> packed [cols][ld_out] (k-major)
+        int64_t o = alloc((int64_t)cols * ld_out);
+        S[name] = Slot{o, (int64_t)rows * cols, [o, rows, cols, ld_out](const float* s, float* d) {
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols; ++c) d[o + (int64_t)c * ld_out + r] = s[(int64_t)r * cols + c];
+        }};
+        return o;
+    };
+    const std::string P = "tfgridnet.";
+    std::vector<std::pair<const float**, int64_t>> fix;   // pointer fields to resolve after alloc
+    auto bind = [&](const float** field, int64_t off) { fix.push_back({field, off}); };
+
+    // STFT filterbanks [194][1][192]
+    bind(&e->w.wat, transposed(P + "enc.filterbank._filters", NROW, NFFT, 196));
+    bind(&e->w.ws, plain(P + "dec.filterbank._filters", (int64_t)NROW * NFFT));
+    bind(&e->w.wc, plain(P + "conv.0.weight", 64 * 36));
+    bind(&e->w.bc, plain(P + "conv.0.bias", 64));
+    bind(&e->w.we, plain(P + "embed_to_feats_proj.0.weight", (int64_t)FC * SPK));
+    bind(&e->w.be, plain(P + "embed_to_feats_proj.0.bias", FC));
+    bind(&e->w.lne_g, plain(P + "embed_to_feats_proj.1.weight", FC));
+    bind(&e->w.lne_b, plain(P + "embed_to_feats_proj.1.bias", FC));
+    bind(&e->w.wd, plain(P + "deconv.weight", 64 * 36));
+    bind(&e->w.bd, plain(P + "deconv.bias", 4));
+
+    e->bw.resize(e->n_blocks);
+    for (int b = 0; b < e->n_blocks; ++b) {
+        BlockWeights& W = e->bw[b];
+        const std::string B = P + "blocks." + std::to_string(b) + ".";
+        bind(&W.ln1_g, plain(B + "intra_norm.norm.weight", 64));
+        bind(&W.ln1_b, plain(B + "intra_norm.norm.bias", 64));
+        bind(&W.ln2_g, plain(B + "inter_norm.norm.weight", 64));
+        bind(&W.ln2_b, plain(B + "inter_norm.norm.bias", 64));
+        // LSTM input weights [256][64] -> Wt[k][dirofs + p], p = j*4+q
+        auto ih = [&](const std::string& name, int64_t base, int ld, int dirofs) {
+            S[name] = Slot{base, 256 * 64, [base, ld, dirofs](const float* s, float* d) {
+                for (int p = 0; p < 256; ++p) {
+                    const int r = perm_row(p);
+                    for (int k = 0; k < 64; ++k) d[base + (int64_t)k * ld + dirofs + p] = s[r * 64 + k];
+                }
+            }};
+        };
+        auto hh = [&](const std::string& name, int64_t base) {
+            S[name] = Slot{base, 256 * 64, [base](const float* s, float* d) {
+                for (int p = 0; p < 256; ++p) memcpy(d + base + (int64_t)p * 64, s + perm_row(p) * 64, 64 * sizeof(float));
+            }};
+        };
+        auto bias = [&](const std::string& name, int64_t base, bool) {
+            Slot sl{base, 256, [base](const float* s, float* d) {
+                for (int p = 0; p < 256; ++p) d[base + p] += s[perm_row(p)];
+            }};
+            sl.accumulate = true;
+            S[name] = sl;
+        };
+        const int64_t wih1 = alloc(64 * 512), b1 = alloc(512), whh1 = alloc(2 * 256 * 64);
+        ih(B + "intra_rnn.weight_ih_l0", wih1, 512, 0);
+        ih(B + "intra_rnn.weight_ih_l0_reverse", wih1, 512, 256);
+        hh(B + "intra_rnn.weight_hh_l0", whh1);
+        hh(B + "intra_rnn.weight_hh_l0_reverse", whh1 + 256 * 64);
+        bias(B + "intra_rnn.bias_ih_l0", b1, true);
+        bias(B + "intra_rnn.bias_hh_l0", b1, true);
+        bias(B + "intra_rnn.bias_ih_l0_reverse", b1 + 256, true);
+        bias(B + "intra_rnn.bias_hh_l0_reverse", b1 + 256, true);
+        bind(&W.wih1_t, wih1); bind(&W.b1, b1); bind(&W.whh1, whh1);
+        bind(&W.wl1_t, transposed(B + "intra_linear.weight", 64, 128, 64));
+        bind(&W.bl1, plain(B + "intra_linear.bias", 64));
+        const int64_t wih2 = alloc(64 * 256), b2 = alloc(256), whh2 = alloc(256 * 64);
+        ih(B + "inter_rnn.weight_ih_l0", wih2, 256, 0);
+        hh(B + "inter_rnn.weight_hh_l0", whh2);
+        bias(B + "inter_rnn.bias_ih_l0", b2, true);
+        bias(B + "inter_rnn.bias_hh_l0", b2, true);
+        bind(&W.wih2_t, wih2); bind(&W.b2, b2); bind(&W.whh2, whh2);
+        bind(&W.wl2_t, transposed(B + "inter_linear.weight", 64, 64, 64));
+        bind(&W.bl2, plain(B + "inter_linear.bias", 64));
+        // Q | K | V projections -> one [64][112] k-major matrix
+        const int64_t wqkv = alloc(64 * NQKV), bqkv = alloc(NQKV), slopes = alloc(4);
+        auto proj = [&](const std::string& mod, int rows, int col0, int slope_idx) {
+            S[B + mod + ".0.weight"] = Slot{wqkv, (int64_t)rows * 64, [wqkv, rows, col0](const float* s, float* d) {
+                for (int r = 0; r < rows; ++r)
+                    for (int k = 0; k < 64; ++k) d[wqkv + (int64_t)k * NQKV + col0 + r] = s[r * 64 + k];
+            }};
+            S[B + mod + ".0.bias"] = Slot{bqkv, rows, [bqkv, rows, col0](const float* s, float* d) {
+                memcpy(d + bqkv + col0, s, rows * sizeof(float));
+            }};
+            S[B + mod + ".1.weight"] = Slot{slopes, 1, [slopes, slope_idx](const float* s, float* d) {
+                d[slopes + slope_idx] = s[0];
+            }};
+        };
+        proj("attn_conv_Q", NHEAD * QE, 0, 0);
+        proj("attn_conv_K", NHEAD * QE, NHEAD * QE, 1);
+        proj("attn_conv_V", NHEAD * VD, 2 * NHEAD * QE, 2);
+        bind(&W.wqkv_t, wqkv); bind(&W.bqkv, bqkv); bind(&W.slopes, slopes);
+        bind(&W.lnq_g, plain(B + "attn_conv_Q.3.norm.weight", QK_DIM));
+        bind(&W.lnq_b, plain(B + "attn_conv_Q.3.norm.bias", QK_DIM));
+        bind(&W.lnk_g, plain(B + "attn_conv_K.3.norm.weight", QK_DIM));
+        bind(&W.lnk_b, plain(B + "attn_conv_K.3.norm.bias", QK_DIM));
+        bind(&W.lnv_g, plain(B + "attn_conv_V.3.norm.weight", V_DIM));
+        bind(&W.lnv_b, plain(B + "attn_conv_V.3.norm.bias", V_DIM));
+        bind(&W.wp_t, transposed(B + "attn_concat_proj.0.weight", 64, 64, 64));
+        bind(&W.bp, plain(B + "attn_concat_proj.0.bias", 64));
+        S[B + "attn_concat_proj.1.weight"] = Slot{slopes, 1, [slopes](const float* s, float* d) { d[slopes + 3] = s[0]; }};
+        bind(&W.lnp_g, plain(B + "attn_concat_proj.3.norm.weight", FC));
+        bind(&W.lnp_b, plain(B + "attn_concat_proj.3.norm.bias", FC));
+    }
+    e->total = cur;
+    e->host.assign(cur, 0.f);
+    // stash offsets in the pointer fields; resolved to device addresses at commit
+    for (auto& f : fix) *f.first = reinterpret_cast<const float*>(f.second);
+}
+
+static void resolve_pointers(SepEngine* e) {
+    auto fixp = [&](const float*& p) { p = e->dev + reinterpret_cast<int64_t>(p); };
+    SepWeights& w = e->w;
+    fixp(w.wat); fixp(w.ws); fixp(w.wc); fixp(w.bc); fixp(w.we); fixp(w.be); fixp(w.lne_g); fixp(w.lne_b);
+    fixp(w.wd); fixp(w.bd);
+    for (auto& W : e->bw) {
+        fixp(W.ln1_g); fixp(W.ln1_b); fixp(W.wih1_t); fixp(W.b1); fixp(W.whh1); fixp(W.wl1_t); fixp(W.bl1);
+        fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.wl2_t); fixp(W.bl2);
+        fixp(W.wqkv_t); fixp(W.bqkv); fixp(W.slopes); fixp(W.lnq_g); fixp(W.lnq_b); fixp(W.lnk_g);
+        fixp(W.lnk_b); fixp(W.lnv_g); fixp(W.lnv_b); fixp(W.wp_t); fixp(W.bp); fixp(W.lnp_g); fixp(W.lnp_b);
+    }
+}
+
+// ---- workspace carve-up (floats) ---------------------------------------------------------------
+struct Workspace {
+    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, TAPS, total;
+};
+static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
+    Workspace ws;
+    const int64_t rows = (int64_t)B * T * NF;
+    int64_t cur = 0;
+    auto alloc = [&](int64_t n) { int64_t o = cur; cur = (cur + n + 31) & ~int64_t(31); return o; };
+    ws.X = alloc(rows * 64);
+    ws.GX = alloc(rows * 512);
+    ws.Y = alloc(rows * 128);
+    ws.Z = alloc(rows * 64);
+    ws.Q = alloc((int64_t)B * NHEAD * T * QK_LD);
+    ws.KALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * QK_LD : 0);
+    ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
+    ws.PRE = alloc((int64_t)B * FC);
+    ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
+    ws.total = cur;
+    return ws;
+}
+
+static bool g_attr_done = false;
+static int set_attrs() {
+    if (g_attr_done) return 0;
+    CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
+    CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
+    CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
+    g_attr_done = true;
+    return 0;
+}
+
+static int sep_forward_impl(SepEngine* e, const float* x, int64_t xbs, int64_t xcs, int x_len, const float* emb,
+                            float* state, float* y, int64_t ybs, int64_t ycs, int y_len, int B, int T,
+                            float* wsp, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+    if (!e->committed) return fail(4, "weights not committed");
+    if (B <= 0 || T <= 0) return fail(1, "batch and frames must be positive");
+    const Workspace ws = carve(e->n_blocks, B, T, flags);
+    if ((size_t)ws.total * sizeof(float) > ws_bytes) return fail(1, "workspace too small");
+    if (int rc = set_attrs()) return rc;
+    const int64_t ss = stream_stride(e->n_blocks);
+    const int64_t rows = (int64_t)B * T * NF;
+    if (rows > 0x7fffffff / 2) return fail(1, "batch*frames too large for one call; split the batch");
+    float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
+    float* Q = wsp + ws.Q; float* KALL = wsp + ws.KALL; float* VALL = wsp + ws.VALL; float* PRE = wsp + ws.PRE;
+    float* TAPS = wsp + ws.TAPS;
+    int tap = 0;
+    auto do_tap = [&]() -> int {
+        if (flags & L2H_FLAG_TAPS) {
+            CK(cudaMemcpyAsync(TAPS + (int64_t)tap * rows * 64, X, rows * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            ++tap;
+        }
+        return 0;
+    };
+    float* sbase = state + sizeof(StateHeader) / 4;
+
+    front_kernel<<<dim3(T, B), 256, 0, st>>>(x, xbs, xcs, x_len, X, state, ss, e->w, T);
+    CK(cudaGetLastError());
+    spk_gemv_kernel<<<dim3(FC / 32, B), 256, 0, st>>>(emb, PRE, state, ss, e->w);
+    CK(cudaGetLastError());
+    spk_ln_kernel<<<B, 256, 0, st>>>(emb, PRE, state, ss, e->w);
+    CK(cudaGetLastError());
+    if (int rc = do_tap()) return rc;
+
+    for (int b = 0; b < e->n_blocks; ++b) {
+        const BlockWeights& W = e->bw[b];
+        // ---- intra: LN -> W_ih (both directions) -> BiLSTM over F -> Linear -> +res ------------
+        GemmArgs g{};
+        g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
+        g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
+        CK(launch_rows_gemm(g, st));
+        LstmArgs l{};
+        l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
+        l.nseq = B * T; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1;
+        l.ndir = 2;
+        CK(launch_lstm_rec(l, st));
+        g = GemmArgs{};
+        g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
+        g.M = (int)rows; g.N = 64; g.K = 128;
+        CK(launch_rows_gemm(g, st));
+        if (int rc = do_tap()) return rc;
+        // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
+        g = GemmArgs{};
+        g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
+        g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
+        CK(launch_rows_gemm(g, st));
+        l = LstmArgs{};
+        l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
+        l.h_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
+        l.c_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_C;
+        l.hc_outer_stride = ss;
+        l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
+        l.step_stride = NF; l.ndir = 1;
+        CK(launch_lstm_rec(l, st));
+        g = GemmArgs{};
+        g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
+        g.M = (int)rows; g.N = 64; g.K = 64;
+        CK(launch_rows_gemm(g, st));
+        if (int rc = do_tap()) return rc;
+        // ---- attention --------------------------------------------------------------------------
+        if (T > 1) {
+            kv_gather_kernel<<<dim3(ATT - 1, B * NHEAD), 128, 0, st>>>(state, ss, b, KALL, VALL, T);
+            CK(cudaGetLastError());
+        }
+        qkv_kernel<<<dim3(T, B), QKV_THREADS, QKV_SMEM, st>>>(X, Q, KALL, VALL, state, ss, b, W, T);
+        CK(cudaGetLastError());
+        attn_kernel<<<dim3(T, NHEAD, B), 256, 0, st>>>(Q, KALL, VALL, state, ss, b, Z, T);
+        CK(cudaGetLastError());
+        attn_out_kernel<<<dim3(T, B), 256, AOUT_SMEM, st>>>(Z, X, state, ss, W, (b == 0 && e->n_blocks > 1) ? 1 : 0, T);
+        CK(cudaGetLastError());
+        if (int rc = do_tap()) return rc;
+    }
+    back_kernel<<<dim3(T, B), 256, BACK_SMEM, st>>>(X, y, ybs, ycs, y_len, state, ss, e->w, T);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace l2h
+
+using namespace l2h;
+
+extern "C" {
+
+int l2h_abi_version(void) { return L2H_ABI_VERSION; }
+const char* l2h_last_error(void) { return g_err.c_str(); }
+
+int l2h_sep_create(const l2h_sep_config* c, void** handle) {
+    if (!c || !handle) return fail(1, "null argument");
+    if (c->stft_chunk_size != HOP || c->stft_pad_size != LOOKAHEAD || c->embed_dim != SPK || c->num_ch != NMIC ||
+        c->D != CH || c->L != NHEAD || c->I != 1 || c->J != 1 || c->H != HID || c->local_atten_len != ATT ||
+        !c->use_attn || !c->lookahead || !c->chunk_causal || c->num_src != NSRC || c->B < 1 || c->B > 16)
+        return fail(1, "unsupported configuration: the kernels are specialised to configs/tsh.json "
+                       "(chunk 128, pad 64, embed 256, 2 ch, D 64, H 64, 4 heads, I=J=1, window 50, 2 src)");
+    SepEngine* e = new SepEngine();
+    e->cfg = *c;
+    e->n_blocks = c->B;
+    build_layout(e);
+    *handle = e;
+    return 0;
+}
+
+int l2h_sep_destroy(void* handle) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return 0;
+    if (e->dev) cudaFree(e->dev);
+    delete e;
+    return 0;
+}
+
+int l2h_sep_load_weight(void* handle, const char* name, const float* data, int64_t numel) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !name || !data) return fail(1, "null argument");
+    auto it = e->slots.find(name);
+    if (it == e->slots.end()) return fail(2, std::string("unknown weight name: ") + name);
+    Slot& s = it->second;
+    if (numel != s.numel) return fail(1, std::string("wrong element count for ") + name);
+    if (s.accumulate) s.raw.assign(data, data + numel);
+    else s.repack(data, e->host.data());
+    s.loaded = true;
+    e->committed = false;
+    return 0;
+}
+
+int l2h_sep_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loaded) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    int n = 0;
+    for (auto& kv : e->slots) n += kv.second.loaded ? 1 : 0;
+    if (n_expected) *n_expected = (int)e->slots.size();
+    if (n_loaded) *n_loaded = n;
+    return 0;
+}
+
+int l2h_sep_commit_weights(void* handle, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    for (auto& kv : e->slots)
+        if (!kv.second.loaded) return fail(4, "weight not loaded: " + kv.first);
+    for (auto& kv : e->slots)
+        if (kv.second.accumulate) std::fill(e->host.begin() + kv.second.off, e->host.begin() + kv.second.off + 256, 0.f);
+    for (auto& kv : e->slots)
+        if (kv.second.accumulate) kv.second.repack(kv.second.raw.data(), e->host.data());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool first = (e->dev == nullptr);
+    if (first) CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
+    CK(cudaMemcpyAsync(e->dev, e->host.data(), e->total * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if (first) resolve_pointers(e);
+    e->committed = true;
+    return 0;
+}
+
+int l2h_sep_state_layout(void* handle, int64_t* header_bytes, int64_t* stride_floats) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    if (header_bytes) *header_bytes = sizeof(StateHeader);
+    if (stride_floats) *stride_floats = stream_stride(e->n_blocks);
+    return 0;
+}
+
+int l2h_sep_state_bytes(void* handle, int32_t batch, size_t* bytes) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !bytes || batch <= 0) return fail(1, "bad argument");
+    *bytes = sizeof(StateHeader) + (size_t)batch * stream_stride(e->n_blocks) * sizeof(float);
+    return 0;
+}
+
+int l2h_sep_state_init(void* handle, void* state, int32_t batch, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !state || batch <= 0) return fail(1, "bad argument");
+    const int64_t ss = stream_stride(e->n_blocks);
+    const int64_t total = sizeof(StateHeader) / 4 + (int64_t)batch * ss;
+    state_init_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(state), total, ss, batch);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int l2h_sep_workspace_bytes(void* handle, int32_t batch, int32_t frames, uint32_t flags, size_t* bytes) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !bytes || batch <= 0 || frames <= 0) return fail(1, "bad argument");
+    *bytes = (size_t)carve(e->n_blocks, batch, frames, flags).total * sizeof(float);
+    return 0;
+}
+
+int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* off, int32_t* n_stages) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    if (off) *off = carve(e->n_blocks, batch, frames, L2H_FLAG_TAPS).TAPS;
+    if (n_stages) *n_stages = 1 + 3 * e->n_blocks;
+    return 0;
+}
+
+int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !n) return fail(1, "bad argument");
+    *n = 3 + e->n_blocks * (9 + (frames > 1 ? 1 : 0)) + 1;
+    return 0;
+}
+
+int l2h_sep_forward(void* handle, const float* x, int64_t xbs, int64_t xcs, int32_t x_len, const float* emb,
+                    void* state, float* y, int64_t ybs, int64_t ycs, int32_t y_len, int32_t batch, int32_t frames,
+                    void* ws, size_t ws_bytes, uint32_t flags, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !x || !emb || !state || !y || !ws) return fail(1, "null argument");
+    return sep_forward_impl(e, x, xbs, xcs, x_len, emb, static_cast<float*>(state), y, ybs, ycs, y_len, batch,
+                            frames, static_cast<float*>(ws), ws_bytes, flags, static_cast<cudaStream_t>(stream));
+}
+
+int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const float* emb, void* state,
+                        float* y_host, int32_t y_len, int32_t batch, int32_t n_calls, int32_t cpc,
+                        float* x_stage, float* y_stage, void* ws, size_t ws_bytes, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !x_host || !emb || !state || !y_host || !x_stage || !y_stage || !ws) return fail(1, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int in_len = HOP * cpc + LOOKAHEAD, out_len = HOP * cpc;
+    for (int i = 0; i < n_calls; ++i) {
+        const int s0 = i * out_len;
+        int n_in = x_len - s0;
+        if (n_in > in_len) n_in = in_len;
+        if (n_in <= 0) return fail(1, "x_host shorter than n_calls * chunks_per_call * 128 samples");
+        CK(cudaMemcpy2DAsync(x_stage, in_len * sizeof(float), x_host + s0, (size_t)x_len * sizeof(float),
+                             (size_t)n_in * sizeof(float), (size_t)batch * NMIC, cudaMemcpyHostToDevice, st));
+        int rc = sep_forward_impl(e, x_stage, (int64_t)NMIC * in_len, in_len, n_in, emb, static_cast<float*>(state),
+                                  y_stage, (int64_t)NSRC * out_len, out_len, out_len, batch, cpc,
+                                  static_cast<float*>(ws), ws_bytes, 0, st);
+        if (rc) return rc;
+        int n_out = y_len - s0;
+        if (n_out > out_len) n_out = out_len;
+        if (n_out > 0)
+            CK(cudaMemcpy2DAsync(y_host + s0, (size_t)y_len * sizeof(float), y_stage, out_len * sizeof(float),
+                                 (size_t)n_out * sizeof(float), (size_t)batch * NSRC, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

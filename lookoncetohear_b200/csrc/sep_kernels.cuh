@@ -1,0 +1,568 @@
+// Separation-network kernels that are not plain row-GEMMs / LSTM recurrences.
+// Reference: /root/reference/src/models/tfgridnet_realtime/tfgridnet_causal.py (cited per kernel).
+// Activations are [B, T, F=97, C=64] fp32 rows of 256 B.
+#pragma once
+#include "common.cuh"
+#include "sep_layout.h"
+
+namespace l2h {
+
+struct SepWeights {           // device pointers into the packed weight buffer
+    const float* wat;         // [192][196]   analysis filters, transposed (n, r)
+    const float* ws;          // [194][192]   synthesis filters (r, n)
+    const float* wc;          // [64][36]     conv (o, c*9+i*3+j)
+    const float* bc;          // [64]
+    const float* we;          // [6208][256]  speaker projection
+    const float* be;          // [6208]
+    const float* lne_g;       // [6208]
+    const float* lne_b;
+    const float* wd;          // [64][4][9]   deconv (c, o, i*3+j)
+    const float* bd;          // [4]
+};
+
+struct BlockWeights {
+    const float *ln1_g, *ln1_b;       // [64]
+    const float* wih1_t;              // [64][512]   (k, dir*256 + j*4+q)
+    const float* b1;                  // [512]       b_ih + b_hh, same packing
+    const float* whh1;                // [2][256][64]
+    const float* wl1_t;               // [128][64]
+    const float* bl1;                 // [64]
+    const float *ln2_g, *ln2_b;
+    const float* wih2_t;              // [64][256]
+    const float* b2;                  // [256]
+    const float* whh2;                // [256][64]
+    const float* wl2_t;               // [64][64]
+    const float* bl2;
+    const float* wqkv_t;              // [64][112]   cols: Q(h*6+e) | K(h*6+e) | V(h*16+c)
+    const float* bqkv;                // [112]
+    const float* slopes;              // [4]  PReLU of Q, K, V, proj
+    const float *lnq_g, *lnq_b;       // [582]
+    const float *lnk_g, *lnk_b;       // [582]
+    const float *lnv_g, *lnv_b;       // [1552]
+    const float* wp_t;                // [64][64]
+    const float* bp;                  // [64]
+    const float *lnp_g, *lnp_b;       // [6208]
+};
+
+// ------------------------------------------------------------------------------------------
+// state init: zero everything, poison the cached embedding with NaN (forces the first gate build)
+__global__ void state_init_kernel(float* state, int64_t total_floats, int64_t stride, int B) {
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t hdr = sizeof(StateHeader) / 4;
+    for (int64_t i = i0; i < total_floats; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i >= hdr) {
+            const int64_t o = (i - hdr) % stride;
+            if (o < SPK) v = __int_as_float(0x7fc00000);
+        }
+        state[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 front: STFT analysis + channel regroup + causal 3x3 conv   (tfgridnet_causal.py:229-242)
+// grid (T, B), 256 threads.  x: [B][NMIC][x_len] (samples past x_len read as zero: the mod-pad and
+// look-ahead zeros of net.py:8-18,56-58).  Frames before the call start come from conv_buf.
+__global__ void __launch_bounds__(256)
+front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
+             float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T) {
+    __shared__ float xs[NMIC][448];
+    __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
+    const int par = (int)(hdr->ncalls & 1);
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float* cb = st + ST_CONV + par * (2 * 4 * NF);
+    float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
+
+    for (int i = tid; i < 3 * 4 * 100; i += 256) (&U[0][0][0])[i] = 0.f;
+    const int s0 = HOP * (t - 2);
+    for (int i = tid; i < NMIC * 448; i += 256) {
+        const int m = i / 448, n = i % 448, s = s0 + n;
+        xs[m][n] = (s >= 0 && s < x_len) ? x[(int64_t)b * x_bstride + (int64_t)m * x_cstride + s] : 0.f;
+    }
+    __syncthreads();
+    // history frames from conv_buf: frame -2 -> slot 0, frame -1 -> slot 1
+    for (int i = 0; i < 2; ++i) {
+        const int tt = t - 2 + i;
+        if (tt < 0)
+            for (int e = tid; e < 4 * NF; e += 256) U[i][e / NF][1 + e % NF] = cb[(2 + tt) * 4 * NF + e];
+    }
+    if (tid < NROW) {
+        float acc[3][NMIC];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+        for (int n = 0; n < NFFT; ++n) {
+            const float wv = __ldg(w.wat + n * 196 + tid);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                acc[i][0] = fmaf(wv, xs[0][HOP * i + n], acc[i][0]);
+                acc[i][1] = fmaf(wv, xs[1][HOP * i + n], acc[i][1]);
+            }
+        }
+        const int ri = tid / NF, f = tid % NF;      // rows 0..96 real, 97..193 imaginary
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (t - 2 + i >= 0) {                   // channels: [Re m0, Re m1, Im m0, Im m1]
+                U[i][ri * 2 + 0][1 + f] = acc[i][0];
+                U[i][ri * 2 + 1][1 + f] = acc[i][1];
+            }
+        }
+    }
+    __syncthreads();
+    // conv: X[f][o] = b_o + sum_{c,i,j} Wc[o][c][i][j] * U[i][c][f-1+j]
+    {
+        const int o = tid & 63, fg = tid >> 6;
+        float wr[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) wr[k] = __ldg(w.wc + o * 36 + k);
+        const float bias = __ldg(w.bc + o);
+        for (int f = fg; f < NF; f += 4) {
+            float acc = bias;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) acc = fmaf(wr[c * 9 + i * 3 + j], U[i][c][f + j], acc);
+            X[(((int64_t)b * T + t) * NF + f) * CH + o] = acc;
+        }
+    }
+    // next conv_buf = spectrogram rows of the last two frames of this call
+    if (T == 1) {
+        for (int e = tid; e < 4 * NF; e += 256) {
+            cb_next[e] = U[1][e / NF][1 + e % NF];
+            cb_next[4 * NF + e] = U[2][e / NF][1 + e % NF];
+        }
+    } else if (t >= T - 2) {
+        const int slot = t - (T - 2);
+        for (int e = tid; e < 4 * NF; e += 256) cb_next[slot * 4 * NF + e] = U[2][e / NF][1 + e % NF];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 speaker gate: g = LN_6208(W e + b), stored (f, c)   (tfgridnet_causal.py:247-248)
+// Memoised on the device: if the embedding equals the one the cached gate was built from, both
+// kernels return immediately (the reference recomputes it every call; results are identical).
+__global__ void __launch_bounds__(256)
+spk_gemv_kernel(const float* __restrict__ emb, float* __restrict__ pre, const float* __restrict__ state,
+                int64_t sstride, SepWeights w) {
+    __shared__ __align__(16) float es[SPK];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float e = emb[(int64_t)b * SPK + tid];
+    const int same = __syncthreads_and(e == st[ST_EMB + tid]);
+    if (same) return;
+    es[tid] = e;
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const float4 e0 = *reinterpret_cast<const float4*>(es + lane * 4);
+    const float4 e1 = *reinterpret_cast<const float4*>(es + 128 + lane * 4);
+    for (int r = 0; r < 4; ++r) {
+        const int n = blockIdx.x * 32 + warp * 4 + r;
+        const float4* wr = reinterpret_cast<const float4*>(w.we + (int64_t)n * SPK);
+        const float4 a0 = __ldg(wr + lane), a1 = __ldg(wr + 32 + lane);
+        float s = a0.x * e0.x + a0.y * e0.y + a0.z * e0.z + a0.w * e0.w +
+                  a1.x * e1.x + a1.y * e1.y + a1.z * e1.z + a1.w * e1.w;
+        s = warp_sum(s);
+        if (lane == 0) pre[(int64_t)b * FC + n] = s + __ldg(w.be + n);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+spk_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pre, float* __restrict__ state,
+              int64_t sstride, SepWeights w) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float e = emb[(int64_t)b * SPK + tid];
+    const int same = __syncthreads_and(e == st[ST_EMB + tid]);
+    if (same) return;
+    const float* p = pre + (int64_t)b * FC;
+    float s = 0.f;
+    for (int i = tid; i < FC; i += 256) s += p[i];
+    const float mu = block_sum(s, red) * (1.f / FC);
+    float q = 0.f;
+    for (int i = tid; i < FC; i += 256) { const float d = p[i] - mu; q += d * d; }
+    const float rs = rsqrtf(block_sum(q, red) * (1.f / FC) + 1e-5f);
+    for (int i = tid; i < FC; i += 256) {          // i = c*97 + f  ->  gate[f][c]
+        const int c = i / NF, f = i % NF;
+        st[ST_GATE + f * CH + c] = (p[i] - mu) * rs * __ldg(w.lne_g + i) + __ldg(w.lne_b + i);
+    }
+    st[ST_EMB + tid] = e;
+}
+
+// ------------------------------------------------------------------------------------------
+// K/V history -> linear scratch for multi-frame calls.  Kall[b*4+h][0..48] = ring slots of frames
+// pos-49 .. pos-1 (never-written slots are zero = the reference's zero-initialised K_buf/V_buf).
+__global__ void kv_gather_kernel(const float* __restrict__ state, int64_t sstride, int blk,
+                                 float* __restrict__ Kall, float* __restrict__ Vall, int T) {
+    const int i = blockIdx.x, bh = blockIdx.y, b = bh / NHEAD, h = bh % NHEAD;
+    const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
+    const long long fr = hdr->pos - (ATT - 1) + i;
+    const int slot = (int)(((fr % ATT) + ATT) % ATT);
+    const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+    const float4* ks = reinterpret_cast<const float4*>(sb + BK_K + ((int64_t)h * ATT + slot) * QK_LD);
+    const float4* vs = reinterpret_cast<const float4*>(sb + BK_V + ((int64_t)h * ATT + slot) * V_DIM);
+    float4* kd = reinterpret_cast<float4*>(Kall + ((int64_t)bh * (ATT - 1 + T) + i) * QK_LD);
+    float4* vd = reinterpret_cast<float4*>(Vall + ((int64_t)bh * (ATT - 1 + T) + i) * V_DIM);
+    const bool live = fr >= 0;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = threadIdx.x; k < QK_LD / 4; k += blockDim.x) kd[k] = live ? ks[k] : z;
+    for (int k = threadIdx.x; k < V_DIM / 4; k += blockDim.x) vd[k] = live ? vs[k] : z;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4a qkv: Linear(64 -> 24|24|64) + PReLU + head split + LayerNorm over (F, E) per head, then
+// append to the K/V history   (tfgridnet_causal.py:547-562, modules :354-387).
+// grid (T, B), 384 threads (12 warps = {Q,K,V} x 4 heads for the LayerNorm phase).
+constexpr int QKV_THREADS = 384;
+constexpr int QKV_PLD = 113;
+constexpr size_t QKV_SMEM = (size_t)(64 * 100 + 64 * NQKV + NF * QKV_PLD) * sizeof(float);
+
+__global__ void __launch_bounds__(QKV_THREADS)
+qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restrict__ Kall,
+           float* __restrict__ Vall, float* __restrict__ state, int64_t sstride, int blk,
+           BlockWeights w, int T) {
+    extern __shared__ __align__(16) float sm[];
+    float* Xt = sm;                      // [64][100]  k-major, rows padded to 100 (zeros)
+    float* Ws = Xt + 64 * 100;           // [64][112]
+    float* P = Ws + 64 * NQKV;           // [97][113]
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const float* xr = X + ((int64_t)b * T + t) * NF * CH;
+    for (int i = tid; i < 100 * 64; i += QKV_THREADS) {
+        const int f = i / 64, k = i % 64;
+        Xt[k * 100 + f] = (f < NF) ? xr[f * CH + k] : 0.f;
+    }
+    for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)
+        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wqkv_t) + i);
+    __syncthreads();
+    // 4 rows x 4 cols register tiles: 25 row groups x 28 col groups
+    for (int it = tid; it < 25 * 28; it += QKV_THREADS) {
+        const int rg = it / 28, cg = it % 28;
+        float2 acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(Xt + k * 100 + rg * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(Ws + k * NQKV + cg * 4);
+            const float2 b0 = make_float2(bb.x, bb.y), b1 = make_float2(bb.z, bb.w);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 aa = make_float2(av[i], av[i]);
+                acc[i][0] = ffma2(aa, b0, acc[i][0]);
+                acc[i][1] = ffma2(aa, b1, acc[i][1]);
+            }
+        }
+        const int n0 = cg * 4;
+        const float slope = __ldg(w.slopes + (n0 < 24 ? 0 : (n0 < 48 ? 1 : 2)));   // 24, 48 are multiples of 4
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(w.bqkv + n0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = rg * 4 + i;
+            if (f < NF) {
+                P[f * QKV_PLD + n0 + 0] = prelu(acc[i][0].x + bias.x, slope);
+                P[f * QKV_PLD + n0 + 1] = prelu(acc[i][0].y + bias.y, slope);
+                P[f * QKV_PLD + n0 + 2] = prelu(acc[i][1].x + bias.z, slope);
+                P[f * QKV_PLD + n0 + 3] = prelu(acc[i][1].y + bias.w, slope);
+            }
+        }
+    }
+    __syncthreads();
+    // LayerNorm per (which, head): one warp each
+    const int warp = tid >> 5, lane = tid & 31;
+    const int which = warp >> 2, h = warp & 3;
+    const int d = (which == 2) ? VD : QE;
+    const int n = NF * d;
+    const int col0 = (which == 2) ? (48 + h * VD) : (which * 24 + h * QE);
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += P[(i / d) * QKV_PLD + col0 + (i % d)];
+    const float mu = warp_sum(s) / (float)n;
+    float q = 0.f;
+    for (int i = lane; i < n; i += 32) { const float dv = P[(i / d) * QKV_PLD + col0 + (i % d)] - mu; q += dv * dv; }
+    const float rs = rsqrtf(warp_sum(q) / (float)n + 1e-5f);
+    const float* gam = (which == 0) ? w.lnq_g : (which == 1 ? w.lnk_g : w.lnv_g);
+    const float* bet = (which == 0) ? w.lnq_b : (which == 1 ? w.lnk_b : w.lnv_b);
+    const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
+    const long long pos = hdr->pos;
+    const int ld = (which == 2) ? V_DIM : QK_LD;
+    float* dst0 = nullptr;   // linear scratch / Q buffer
+    float* dst1 = nullptr;   // ring slot
+    const int64_t bh = (int64_t)b * NHEAD + h;
+    if (which == 0) {
+        dst0 = Qbuf + (bh * T + t) * QK_LD;
+    } else {
+        float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+        const int slot = (int)((pos + t) % ATT);
+        if (t >= T - ATT)
+            dst1 = sb + (which == 1 ? BK_K : BK_V) + ((int64_t)h * ATT + slot) * ld;
+        if (T > 1) dst0 = (which == 1 ? Kall : Vall) + (bh * (ATT - 1 + T) + (ATT - 1) + t) * ld;
+    }
+    for (int i = lane; i < n; i += 32) {
+        const float v = (P[(i / d) * QKV_PLD + col0 + (i % d)] - mu) * rs * __ldg(gam + i) + __ldg(bet + i);
+        if (dst0) dst0[i] = v;
+        if (dst1) dst1[i] = v;
+    }
+    if (which != 2 && lane < 2) {        // zero the two pad columns of 582 -> 584
+        if (dst0) dst0[QK_DIM + lane] = 0.f;
+        if (dst1) dst1[QK_DIM + lane] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4b local attention: each query attends to its own frame + the 49 previous ones, unmasked
+// (tfgridnet_causal.py:564-581).  grid (T, 4, B), 256 threads.
+// T == 1: K/V rows are the 50 ring slots (order is irrelevant to softmax-weighted sums);
+// T  > 1: rows t .. t+49 of the linear scratch.
+__global__ void __launch_bounds__(256)
+attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
+            const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T) {
+    __shared__ __align__(16) float qs[QK_LD];
+    __shared__ float sc[64];
+    const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    const int64_t bh = (int64_t)b * NHEAD + h;
+    const float* kb;
+    const float* vb;
+    if (T == 1) {
+        const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+        kb = sb + BK_K + (int64_t)h * ATT * QK_LD;
+        vb = sb + BK_V + (int64_t)h * ATT * V_DIM;
+    } else {
+        kb = Kall + (bh * (ATT - 1 + T) + t) * QK_LD;
+        vb = Vall + (bh * (ATT - 1 + T) + t) * V_DIM;
+    }
+    const float* q = Qbuf + (bh * T + t) * QK_LD;
+    for (int i = tid; i < QK_LD / 4; i += 256)
+        reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(q)[i];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const float scale = rsqrtf((float)QK_DIM);
+    for (int j = warp; j < ATT; j += 8) {
+        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)j * QK_LD);
+        float s = 0.f;
+        for (int i = lane; i < QK_LD / 4; i += 32) {
+            const float4 kv = kr[i];
+            const float4 qv = reinterpret_cast<const float4*>(qs)[i];
+            s += kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w;
+        }
+        s = warp_sum(s);
+        if (lane == 0) sc[j] = s * scale;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float a0 = (lane < ATT) ? sc[lane] : -INFINITY;
+        const float a1 = (lane + 32 < ATT) ? sc[lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(a0, a1));
+        const float e0 = (lane < ATT) ? __expf(a0 - mx) : 0.f;
+        const float e1 = (lane + 32 < ATT) ? __expf(a1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        if (lane < ATT) sc[lane] = e0 * inv;
+        if (lane + 32 < ATT) sc[lane + 32] = e1 * inv;
+    }
+    __syncthreads();
+    float* zr = Z + ((int64_t)b * T + t) * NF * CH;
+    for (int c4 = tid; c4 < V_DIM / 4; c4 += 256) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 10
+        for (int j = 0; j < ATT; ++j) {
+            const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4];
+            const float p = sc[j];
+            acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
+            acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+        }
+        const int f = c4 >> 2, c0 = (c4 & 3) * 4;            // feature f*16 + c -> channel h*16 + c
+        *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4c attention output: Linear(64->64) + PReLU + LayerNorm over (F, C) + residual
+// (tfgridnet_causal.py:583-588); for block 0 the speaker gate that the reference applies to the
+// input of block 1 (:250-251) is folded into this epilogue.  grid (T, B), 256 threads.
+constexpr size_t AOUT_SMEM = (size_t)(64 * 100 + 64 * 64 + NF * 64) * sizeof(float);
+
+__global__ void __launch_bounds__(256)
+attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float* __restrict__ state,
+                int64_t sstride, BlockWeights w, int apply_gate, int T) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float red[32];
+    float* Zt = sm;                 // [64][100]
+    float* Ws = Zt + 64 * 100;      // [64][64]
+    float* P = Ws + 64 * 64;        // [97][64]
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
+    for (int i = tid; i < 100 * 64; i += 256) {
+        const int f = i / 64, k = i % 64;
+        Zt[k * 100 + f] = (f < NF) ? zr[f * CH + k] : 0.f;
+    }
+    for (int i = tid; i < 64 * 64 / 4; i += 256)
+        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wp_t) + i);
+    __syncthreads();
+    const float slope = __ldg(w.slopes + 3);
+    for (int it = tid; it < 25 * 16; it += 256) {
+        const int rg = it / 16, cg = it % 16;
+        float2 acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(Zt + k * 100 + rg * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(Ws + k * 64 + cg * 4);
+            const float2 b0 = make_float2(bb.x, bb.y), b1 = make_float2(bb.z, bb.w);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 aa = make_float2(av[i], av[i]);
+                acc[i][0] = ffma2(aa, b0, acc[i][0]);
+                acc[i][1] = ffma2(aa, b1, acc[i][1]);
+            }
+        }
+        const int n0 = cg * 4;
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(w.bp + n0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = rg * 4 + i;
+            if (f < NF) {
+                float4 o;
+                o.x = prelu(acc[i][0].x + bias.x, slope);
+                o.y = prelu(acc[i][0].y + bias.y, slope);
+                o.z = prelu(acc[i][1].x + bias.z, slope);
+                o.w = prelu(acc[i][1].y + bias.w, slope);
+                *reinterpret_cast<float4*>(P + f * 64 + n0) = o;
+            }
+        }
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = tid; i < FC; i += 256) s += P[i];
+    const float mu = block_sum(s, red) * (1.f / FC);
+    float q = 0.f;
+    for (int i = tid; i < FC; i += 256) { const float d = P[i] - mu; q += d * d; }
+    const float rs = rsqrtf(block_sum(q, red) * (1.f / FC) + 1e-5f);
+    float* xr = X + ((int64_t)b * T + t) * NF * CH;
+    const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
+    for (int i = tid; i < FC; i += 256) {
+        float v = xr[i] + (P[i] - mu) * rs * __ldg(w.lnp_g + i) + __ldg(w.lnp_b + i);
+        if (apply_gate) v *= gate[i];
+        xr[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 back: causal 3x3 transposed conv (64 -> 4) + Re/Im regroup + synthesis filterbank +
+// overlap-add   (tfgridnet_causal.py:256-273; net.py:61 drops the look-ahead tail).
+// grid (T, B), 256 threads.  y: [B][NSRC][y_len], frame t writes samples 128 t .. 128 t + 127.
+// The last CTA to finish advances the state header (pos += T, ncalls += 1).
+constexpr size_t BACK_SMEM = (size_t)(4 * 99 * 64 + 2 * NSRC * NROW + NSRC * HOP + NSRC * LOOKAHEAD) * sizeof(float);
+
+__global__ void __launch_bounds__(256)
+back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
+            int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T) {
+    extern __shared__ __align__(16) float sm[];
+    float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]
+    float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
+    float* outs = R + 2 * NSRC * NROW;    // [2 ears][128]
+    float* tails = outs + NSRC * HOP;     // [2 ears][64]  w_{t-1}[128..191]
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
+    const int par = (int)(hdr->ncalls & 1);
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float* db = st + ST_DECONV + par * (2 * FC);
+    float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
+    const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
+    float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
+
+    for (int i = tid; i < 4 * 99 * 64; i += 256) {
+        const int slot = i / (99 * 64), r = (i / 64) % 99, c = i % 64;
+        const int tt = t - 3 + slot, f = r - 1;
+        float v = 0.f;
+        if (f >= 0 && f < NF) {
+            if (tt >= 0) v = X[(((int64_t)b * T + tt) * NF + f) * CH + c];
+            else if (tt >= -2) v = db[(2 + tt) * FC + f * CH + c];
+        }
+        Xs[i] = v;
+    }
+    __syncthreads();
+    // deconv for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        float wr[2][36];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 36; ++k) wr[u][k] = __ldg(w.wd + (lane + 32 * u) * 36 + k);
+        for (int fi = (t >= 1 ? 0 : 1); fi < 2; ++fi) {
+            for (int f = warp; f < NF; f += 8) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        // frame (t-1+fi) - i  -> slot (2 + fi - i) ; freq f+1-j -> padded row f+2-j
+                        const float* xp = Xs + ((2 + fi - i) * 99 + (f + 2 - j)) * 64;
+                        const float x0 = xp[lane], x1 = xp[lane + 32];
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            acc[o] = fmaf(wr[0][o * 9 + i * 3 + j], x0, acc[o]);
+                            acc[o] = fmaf(wr[1][o * 9 + i * 3 + j], x1, acc[o]);
+                        }
+                    }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float v = warp_sum(acc[o]);
+                    // channel o = 2*ear + ri  ->  R[ear][ri*97 + f]
+                    if (lane == 0) R[(fi * NSRC + (o >> 1)) * NROW + (o & 1) * NF + f] = v + __ldg(w.bd + o);
+                }
+            }
+        }
+        if (t == 0)
+            for (int i = tid; i < NSRC * NROW; i += 256) R[i] = ib[i];
+    }
+    __syncthreads();
+    // synthesis + overlap-add: out[n] = w_t[n] + w_{t-1}[128 + n] (n < 64)
+    for (int i = tid; i < NSRC * NFFT; i += 256) {
+        const int ear = i / NFFT, n = i % NFFT;
+        const int fi = (n < HOP) ? 1 : 0;
+        const float* rr = R + (fi * NSRC + ear) * NROW;
+        float acc = 0.f;
+        for (int r = 0; r < NROW; ++r) acc = fmaf(rr[r], __ldg(w.ws + r * NFFT + n), acc);
+        if (n < HOP) outs[ear * HOP + n] = acc;
+        else tails[ear * LOOKAHEAD + (n - HOP)] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < NSRC * HOP; i += 256) {
+        const int ear = i / HOP, n = i % HOP;
+        const int s = HOP * t + n;
+        if (s < y_len) {
+            float v = outs[i];
+            if (n < LOOKAHEAD) v += tails[ear * LOOKAHEAD + n];
+            y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
+        }
+    }
+    // next tails
+    if (T == 1) {
+        for (int i = tid; i < FC; i += 256) {
+            db_next[i] = Xs[(2 * 99 + 1) * 64 + i];            // frame -1 (slot 2), rows 1..97 contiguous
+            db_next[FC + i] = Xs[(3 * 99 + 1) * 64 + i];       // frame 0
+        }
+    } else if (t >= T - 2) {
+        for (int i = tid; i < FC; i += 256) db_next[(t - (T - 2)) * FC + i] = Xs[(3 * 99 + 1) * 64 + i];
+    }
+    if (t == T - 1)
+        for (int i = tid; i < NSRC * NROW; i += 256) ib_next[i] = R[NSRC * NROW + i];
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int prev = atomicAdd(&hdr->done, 1);
+        if (prev == (int)(gridDim.x * gridDim.y) - 1) {
+            hdr->pos += T;
+            hdr->ncalls += 1;
+            hdr->done = 0;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace l2h

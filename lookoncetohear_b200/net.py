@@ -1,0 +1,356 @@
+"""Drop-in for ``src.models.tfgridnet_realtime.net.Net`` (reference net.py:20-76).
+
+Select it from the reference's config by pointing ``pl_module_args.model`` at
+``lookoncetohear_b200.net.Net`` (the plugin boundary is ``utils.import_attr`` at
+ts_hear_embed_pl_module.py:25).  Same constructor keywords, same parameter names and shapes (a
+Lightning checkpoint's ``state_dict`` loads unchanged), same ``forward / predict /
+init_buffers`` signatures.  The arithmetic is NOT here: every call goes through the C ABI of
+``liblookonce_b200.so`` (hand-written sm_100a CUDA).  There is no PyTorch/CPU fallback -- on a
+machine without the built library or without a CUDA device the calls raise.
+
+The torch modules held below (nn.Conv2d, nn.LSTM, ...) are used purely as parameter containers,
+so names / shapes / default initialisation match the reference; their ``forward`` is never run.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+_HOP_DEFAULT = 128
+
+
+class _Filterbank(nn.Module):
+    """Holds the STFT filter matrix as a buffer named like asteroid's ``filterbank._filters``
+    (tfgridnet_causal.py:131-135).  Values: sqrt-periodic-Hann windowed, scaled DFT rows
+    (Re rows 0..N/2, then Im rows), as asteroid_filterbanks.STFTFB builds them."""
+
+    def __init__(self, n_filters, kernel_size, stride):
+        super().__init__()
+        n = torch.arange(kernel_size, dtype=torch.float64)
+        k = torch.arange(n_filters // 2 + 1, dtype=torch.float64)
+        win = torch.sqrt(0.5 - 0.5 * torch.cos(2 * math.pi * n / kernel_size))
+        ang = 2 * math.pi * k[:, None] * n[None, :] / n_filters
+        scale = 1.0 / (0.5 * math.sqrt(kernel_size * n_filters / stride))
+        filt = torch.cat([torch.cos(ang), -torch.sin(ang)], dim=0) * scale
+        filt[0] /= math.sqrt(2.0)
+        filt[n_filters // 2] /= math.sqrt(2.0)
+        self.register_buffer("_filters", (filt * win).unsqueeze(1).float())
+
+
+class _Codec(nn.Module):
+    def __init__(self, n_filters, kernel_size, stride):
+        super().__init__()
+        self.filterbank = _Filterbank(n_filters, kernel_size, stride)
+
+
+class _LN(nn.Module):
+    """Same names as the reference's LayerNormalization4D / 4DCF wrappers (``.norm.weight``)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.norm = nn.LayerNorm(n)
+
+
+def _attn_branch(emb_dim, out_dim, ln_dim):
+    # indices 0 (Linear), 1 (PReLU), 2 (parameter-less reshape), 3 (LayerNorm) as in the reference
+    return nn.Sequential(nn.Linear(emb_dim, out_dim), nn.PReLU(), nn.Identity(), _LN(ln_dim))
+
+
+class _BlockParams(nn.Module):
+    """Parameter container for one GridNetBlock (tfgridnet_causal.py:301-401), same creation
+    order as the reference so seeded default init reproduces the same values."""
+
+    def __init__(self, emb_dim, n_freqs, hidden, n_head, approx_qk_dim=512):
+        super().__init__()
+        E = math.ceil(approx_qk_dim * 1.0 / n_freqs)
+        self.intra_norm = _LN(emb_dim)
+        self.intra_rnn = nn.LSTM(emb_dim, hidden, 1, batch_first=True, bidirectional=True)
+        self.intra_linear = nn.Linear(hidden * 2, emb_dim)
+        self.inter_norm = _LN(emb_dim)
+        self.inter_rnn = nn.LSTM(emb_dim, hidden, 1, batch_first=True, bidirectional=False)
+        self.inter_linear = nn.Linear(hidden, emb_dim)
+        self.attn_conv_Q = _attn_branch(emb_dim, E * n_head, n_freqs * E)
+        self.attn_conv_K = _attn_branch(emb_dim, E * n_head, n_freqs * E)
+        self.attn_conv_V = _attn_branch(emb_dim, (emb_dim // n_head) * n_head, n_freqs * (emb_dim // n_head))
+        self.attn_concat_proj = _attn_branch(emb_dim, emb_dim, n_freqs * emb_dim)
+
+
+class _TFGridNetParams(nn.Module):
+    def __init__(self, n_fft, stride, spk_emb_dim, emb_dim, n_layers, n_imics, n_srcs, hidden, n_head):
+        super().__init__()
+        n_freqs = n_fft // 2 + 1
+        self.enc = _Codec(n_fft, n_fft, stride)
+        self.dec = _Codec(n_fft, n_fft, stride)
+        self.conv = nn.Sequential(nn.Conv2d(2 * n_imics, emb_dim, (3, 3), padding=(0, 1)))
+        self.blocks = nn.ModuleList([_BlockParams(emb_dim, n_freqs, hidden, n_head) for _ in range(n_layers)])
+        self.embed_to_feats_proj = nn.Sequential(nn.Linear(spk_emb_dim, emb_dim * n_freqs),
+                                                 nn.LayerNorm(emb_dim * n_freqs))
+        self.deconv = nn.ConvTranspose2d(emb_dim, n_srcs * 2, (3, 3), padding=(2, 1))
+
+
+class SepState(dict):
+    """The streaming state returned by ``Net.init_buffers`` and threaded through ``predict``.
+
+    One contiguous device allocation (header + per-stream records, layout in csrc/sep_layout.h)
+    that the kernels update in place; the dict interface is kept because reference callers treat
+    the state as an opaque dict they pass back.  ``to_reference()`` / ``load_reference()``
+    convert to/from the reference's nested dict of tensors (tfgridnet_causal.py:173-186,408-427).
+    """
+
+    def __init__(self, buf, batch, n_blocks, header_bytes, stride):
+        super().__init__()
+        self.buf, self.batch, self.n_blocks = buf, batch, n_blocks
+        self.header_floats, self.stride = header_bytes // 4, stride
+        self["buf"] = buf
+
+    # ---- views ------------------------------------------------------------------------------
+    def _rec(self):
+        return self.buf[self.header_floats:].view(self.batch, self.stride)
+
+    def header(self):
+        """(pos, ncalls) -- synchronises."""
+        h = self.buf[:4].view(torch.int64).cpu()
+        return int(h[0]), int(h[1])
+
+    _F, _C, _ATT, _QKLD, _QK, _VD, _NH = 97, 64, 50, 584, 582, 1552, 4
+    _ST_GATE = 256
+    _ST_CONV = 256 + 6208
+    _ST_DECONV = _ST_CONV + 2 * 2 * 4 * 97
+    _ST_ISTFT = _ST_DECONV + 2 * 2 * 6208
+    _ST_BLK = _ST_ISTFT + 2 * 2 * 194
+    _BK_V = 4 * 50 * 584
+    _BK_H = _BK_V + 4 * 50 * 1552
+    _BK_C = _BK_H + 6208
+    _BK_STRIDE = _BK_C + 6208
+
+    def to_reference(self):
+        """Nested dict with the reference's keys and shapes (copies; synchronises)."""
+        pos, ncalls = self.header()
+        par = ncalls & 1
+        r, B = self._rec(), self.batch
+        conv = r[:, self._ST_CONV:self._ST_DECONV].view(B, 2, 2, 4, 97)[:, par]            # [B,slot,ch,F]
+        deconv = r[:, self._ST_DECONV:self._ST_ISTFT].view(B, 2, 2, 97, 64)[:, par]        # [B,slot,F,C]
+        istft = r[:, self._ST_ISTFT:self._ST_BLK].view(B, 2, 2, 194)[:, par]               # [B,ear,2F]
+        out = dict(conv_buf=conv.permute(0, 2, 1, 3).contiguous(),
+                   deconv_buf=deconv.permute(0, 3, 1, 2).contiguous(),
+                   istft_buf=istft.unsqueeze(-1).contiguous(), gridnet_bufs={})
+        # ring slot of frame n is n % 50; history rows are frames pos-49 .. pos-1
+        frames = torch.arange(pos - 49, pos)
+        slots = torch.remainder(frames, 50).to(self.buf.device)
+        live = (frames >= 0).to(self.buf.device, self.buf.dtype)[None, None, :, None]
+        for i in range(self.n_blocks):
+            o = self._ST_BLK + i * self._BK_STRIDE
+            K = r[:, o:o + self._BK_V].view(B, 4, 50, 584)[:, :, :, :582]
+            V = r[:, o + self._BK_V:o + self._BK_H].view(B, 4, 50, 1552)
+            out["gridnet_bufs"][f"buf{i}"] = dict(
+                K_buf=(K[:, :, slots] * live).reshape(B * 4, 49, 582).contiguous(),
+                V_buf=(V[:, :, slots] * live).reshape(B * 4, 49, 1552).contiguous(),
+                h0=r[:, o + self._BK_H:o + self._BK_C].reshape(1, B * 97, 64).clone(),
+                c0=r[:, o + self._BK_C:o + self._BK_STRIDE].reshape(1, B * 97, 64).clone())
+        return out
+
+
+class Net(nn.Module):
+    """B200-native replacement of the reference ``Net`` (net.py:20-76)."""
+
+    def __init__(self, stft_chunk_size=160, stft_pad_size=120, embed_dim=256, num_ch=2, D=64, B=6, I=1, J=1,
+                 L=0, H=128, use_attn=False, lookahead=True, local_atten_len=100, chunk_causal=False,
+                 num_src=2):
+        super().__init__()
+        self.stft_chunk_size = stft_chunk_size
+        self.stft_pad_size = stft_pad_size
+        self.num_ch = num_ch
+        self.lookahead = lookahead
+        self.nfft = stft_chunk_size + stft_pad_size
+        self._cfg = _cabi.SepConfig(stft_chunk_size, stft_pad_size, embed_dim, num_ch, D, L, I, J, B, H,
+                                    local_atten_len, int(bool(use_attn)), int(bool(lookahead)),
+                                    int(bool(chunk_causal)), num_src)
+        self.num_src, self.embed_dim, self.n_blocks = num_src, embed_dim, B
+        self.tfgridnet = _TFGridNetParams(self.nfft, stft_chunk_size, embed_dim, D, B, num_ch, num_src, H,
+                                          max(L, 1))
+        self._handle = None
+        self._dirty = True                      # weights need (re)packing into the engine
+        self._ws = None
+        self.max_frames_per_launch = 8192       # batch*frames per kernel chain (workspace bound)
+
+    # ---- engine plumbing -------------------------------------------------------------------
+    def _engine(self):
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            _cabi.check(_cabi.lib().l2h_sep_create(ctypes.byref(self._cfg), ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _cabi.lib().l2h_sep_destroy(self._handle)
+        except Exception:
+            pass
+
+    def refresh_weights(self):
+        """Call after editing parameters in place; load_state_dict / .to() / .cuda() do it themselves."""
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):
+        self._dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def _sync_weights(self, device):
+        """(Re)pack the weights into the engine after construction, load_state_dict or .to()."""
+        if not self._dirty:
+            return
+        tensors = dict(self.state_dict())
+        h, L = self._engine(), _cabi.lib()
+        for name, t in tensors.items():
+            if name.endswith("torch_window"):
+                continue
+            host = t.detach().to("cpu", torch.float32).contiguous()
+            _cabi.check(L.l2h_sep_load_weight(h, name.encode(), host.data_ptr(), host.numel()))
+        with torch.cuda.device(device):
+            _cabi.check(L.l2h_sep_commit_weights(h, torch.cuda.current_stream(device).cuda_stream))
+        self._dirty = False
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # real asteroid registers an extra (redundant) window buffer on the filterbank; accept it
+        for k in [k for k in state_dict if k.startswith(prefix) and k.endswith("filterbank.torch_window")]:
+            state_dict.pop(k)
+        self._dirty = True
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _workspace(self, device, batch, frames, flags=0):
+        n = ctypes.c_size_t()
+        _cabi.check(_cabi.lib().l2h_sep_workspace_bytes(self._engine(), batch, frames, flags, ctypes.byref(n)))
+        if self._ws is None or self._ws.numel() < n.value or self._ws.device != device:
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+        return self._ws, n.value
+
+    @staticmethod
+    def _require_cuda(t):
+        if not t.is_cuda:
+            raise RuntimeError("lookoncetohear_b200.Net runs only on a CUDA (sm_100a) device: the hot path is "
+                               "hand-written CUDA with no CPU fallback")
+
+    # ---- reference API ---------------------------------------------------------------------
+    def init_buffers(self, batch_size, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("lookoncetohear_b200.Net.init_buffers: CUDA device required (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        L, h = _cabi.lib(), self._engine()
+        n = ctypes.c_size_t()
+        _cabi.check(L.l2h_sep_state_bytes(h, batch_size, ctypes.byref(n)))
+        hb, stride = ctypes.c_int64(), ctypes.c_int64()
+        _cabi.check(L.l2h_sep_state_layout(h, ctypes.byref(hb), ctypes.byref(stride)))
+        buf = torch.empty(n.value // 4, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _cabi.check(L.l2h_sep_state_init(h, buf.data_ptr(), batch_size,
+                                             torch.cuda.current_stream(device).cuda_stream))
+        return SepState(buf, batch_size, self.n_blocks, hb.value, stride.value)
+
+    def _run(self, x, embed, state, frames, out_len, flags=0):
+        """x [B,M,n] (any length; samples beyond n read as zero), embed [B,256]."""
+        self._require_cuda(x)
+        dev = x.device
+        self._sync_weights(dev)
+        x = x.contiguous().float()
+        embed = embed.to(dev, torch.float32).contiguous()
+        Bsz = x.shape[0]
+        if state.batch != Bsz:
+            raise ValueError(f"state was built for batch {state.batch}, input has batch {Bsz}")
+        y = torch.empty(Bsz, self.num_src, out_len, dtype=torch.float32, device=dev)
+        ws, nbytes = self._workspace(dev, Bsz, frames, flags)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().l2h_sep_forward(
+                self._engine(), x.data_ptr(), x.stride(0), x.stride(1), x.shape[-1], embed.data_ptr(),
+                state.buf.data_ptr(), y.data_ptr(), y.stride(0), y.stride(1), out_len, Bsz, frames,
+                ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream(dev).cuda_stream))
+        return y
+
+    def predict(self, x, embed, input_state, pad=True):
+        """Reference net.py:54-66.  x [B,M,N]; embed [B,256]; returns (y [B,S,*], state)."""
+        hop, la = self.stft_chunk_size, self.stft_pad_size
+        n = x.shape[-1]
+        if pad:
+            frames = (n + hop - 1) // hop          # mod-pad to whole hops, + look-ahead zeros
+            out_len = n
+        else:
+            if (n - la) % hop != 0 or n < hop + la:
+                raise ValueError(f"pad=False needs {hop}*T+{la} samples, got {n}")
+            frames = (n - la) // hop
+            out_len = frames * hop
+        if not isinstance(input_state, SepState):
+            raise TypeError("input_state must come from Net.init_buffers()")
+        y = self._run(x, embed, input_state, frames, out_len)
+        return y, input_state
+
+    def forward(self, x, embeds, input_state=None, pad=True):
+        """Reference net.py:68-76.  x [B,M,N]; embeds [B,1,256] -> [B,S,N]."""
+        embeds = embeds[:, 0]
+        Bsz = x.shape[0]
+        hop = self.stft_chunk_size
+        frames = (x.shape[-1] + hop - 1) // hop
+        # independent streams: split the batch so batch*frames stays inside the workspace bound
+        per = max(1, self.max_frames_per_launch // max(frames, 1))
+        if input_state is not None or Bsz <= per:
+            if input_state is None:
+                input_state = self.init_buffers(Bsz, x.device)
+            y, _ = self.predict(x, embeds, input_state, pad)
+            return y
+        outs = []
+        for b0 in range(0, Bsz, per):
+            xs, es = x[b0:b0 + per], embeds[b0:b0 + per]
+            st = self.init_buffers(xs.shape[0], x.device)
+            outs.append(self.predict(xs, es, st, pad)[0])
+        return torch.cat(outs, dim=0)
+
+    def stream_host(self, x_host, embed_dev, chunks_per_call=1, state=None):
+        """End-to-end streaming with HOST buffers (l2h_sep_stream_host): x_host [B,M,N] CPU tensor
+        (pinned here if it is not), every call copies its chunk host->device, runs the chain and
+        copies the new samples back; returns y [B,S,128*n_calls*chunks_per_call] on the host."""
+        dev = embed_dev.device
+        self._require_cuda(embed_dev)
+        self._sync_weights(dev)
+        hop, la = self.stft_chunk_size, self.stft_pad_size
+        Bsz, _, n = x_host.shape
+        step = hop * chunks_per_call
+        n_calls = (n + step - 1) // step
+        xh = x_host.contiguous().float()
+        if not xh.is_pinned():
+            xh = xh.pin_memory()
+        yh = torch.empty(Bsz, self.num_src, n_calls * step, dtype=torch.float32).pin_memory()
+        if state is None:
+            state = self.init_buffers(Bsz, dev)
+        xs = torch.empty(Bsz, self.num_ch, step + la, dtype=torch.float32, device=dev)
+        ys = torch.empty(Bsz, self.num_src, step, dtype=torch.float32, device=dev)
+        ws, _ = self._workspace(dev, Bsz, chunks_per_call)
+        emb = embed_dev.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().l2h_sep_stream_host(
+                self._engine(), xh.data_ptr(), n, emb.data_ptr(), state.buf.data_ptr(), yh.data_ptr(),
+                yh.shape[-1], Bsz, n_calls, chunks_per_call, xs.data_ptr(), ys.data_ptr(), ws.data_ptr(),
+                ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        self._last_stream_state = state
+        return yh[..., :n]
+
+    # ---- debugging aid for the parity tests ------------------------------------------------------
+    def forward_with_taps(self, x, embeds):
+        """Whole-utterance forward that also returns the activations after every stage
+        ([B,T,97,64] each): encoder, then per block (after intra, after inter, block output)."""
+        embeds = embeds[:, 0]
+        hop = self.stft_chunk_size
+        frames = (x.shape[-1] + hop - 1) // hop
+        st = self.init_buffers(x.shape[0], x.device)
+        y = self._run(x, embeds, st, frames, x.shape[-1], flags=1)
+        off, ns = ctypes.c_int64(), ctypes.c_int32()
+        _cabi.check(_cabi.lib().l2h_sep_tap_info(self._engine(), x.shape[0], frames, ctypes.byref(off),
+                                                ctypes.byref(ns)))
+        n = x.shape[0] * frames * 97 * 64
+        wsf = self._ws.view(torch.float32)
+        taps = [wsf[off.value + i * n: off.value + (i + 1) * n].view(x.shape[0], frames, 97, 64).clone()
+                for i in range(ns.value)]
+        return y, taps, st

@@ -1,0 +1,1 @@
+"""ORACLE SHIM package (test infrastructure)."""

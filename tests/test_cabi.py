@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports every
+symbol include/*.h declares; host-only entry points behave (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lookoncetohear_b200 import build, _cabi
+    build.build()
+    return _cabi.lib()
+
+
+def _declared():
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        if fn.endswith(".h"):
+            txt = open(os.path.join(inc, fn)).read()
+            txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+            names += re.findall(r"\b(l2h_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+
+
+def test_binding_covers_header(lib):
+    from lookoncetohear_b200 import _cabi
+    assert set(_declared()) == set(_cabi.declared_symbols())
+
+
+def test_create_rejects_other_configs(lib):
+    from lookoncetohear_b200 import _cabi
+    bad = _cabi.SepConfig(160, 120, 256, 2, 64, 4, 1, 1, 3, 64, 50, 1, 1, 1, 2)
+    h = ctypes.c_void_p()
+    assert lib.l2h_sep_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"unsupported" in lib.l2h_last_error()
+
+
+def test_weight_table_matches_reference_state_dict(lib, tsh_params):
+    """Every key of the (mirror) state_dict is accepted, the expected count is reached, unknown
+    names and wrong sizes are refused -- all host-side, no GPU."""
+    from lookoncetohear_b200 import Net
+    net = Net(**tsh_params)
+    h = net._engine()
+    for k, v in net.state_dict().items():
+        host = v.detach().float().contiguous()
+        assert lib.l2h_sep_load_weight(h, k.encode(), host.data_ptr(), host.numel()) == 0, k
+    ne, nl = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.l2h_sep_weights_expected(h, ctypes.byref(ne), ctypes.byref(nl)) == 0
+    assert ne.value == nl.value == len(net.state_dict())
+    z = torch.zeros(4)
+    assert lib.l2h_sep_load_weight(h, b"tfgridnet.nope", z.data_ptr(), 4) == 2
+    assert lib.l2h_sep_load_weight(h, b"tfgridnet.deconv.bias", z.data_ptr(), 3) == 1
+
+
+def test_state_and_workspace_sizes(lib, tsh_params):
+    from lookoncetohear_b200 import Net
+    net = Net(**tsh_params)
+    h = net._engine()
+    n = ctypes.c_size_t()
+    assert lib.l2h_sep_state_bytes(h, 1, ctypes.byref(n)) == 0
+    # reference state is 5,222,480 B/stream; ours adds the cached gate, the padded
+    # K rows, one extra ring slot and the double-buffered tails
+    assert 5_222_480 < n.value < 5_600_000
+    n2 = ctypes.c_size_t()
+    assert lib.l2h_sep_state_bytes(h, 3, ctypes.byref(n2)) == 0
+    assert (n2.value - 64) == 3 * (n.value - 64)
+    w = ctypes.c_size_t()
+    assert lib.l2h_sep_workspace_bytes(h, 1, 1, 0, ctypes.byref(w)) == 0 and w.value > 0
+
+
+def test_cpu_tensors_are_refused(tsh_params):
+    """No CPU fallback: the module raises instead of computing on the host."""
+    from lookoncetohear_b200 import Net
+    net = Net(**tsh_params)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 256), torch.zeros(1, 1, 256))
+    with pytest.raises(RuntimeError):
+        net.init_buffers(1, "cpu")
+
+
+def test_mirror_module_matches_reference_layout(tsh_params):
+    from lookoncetohear_b200 import Net
+    net = Net(**tsh_params)
+    assert sum(p.numel() for p in net.parameters()) == 2_037_960
+    sd = net.state_dict()
+    assert tuple(sd["tfgridnet.enc.filterbank._filters"].shape) == (194, 1, 192)
+    assert tuple(sd["tfgridnet.blocks.2.attn_conv_V.3.norm.weight"].shape) == (1552,)
+    assert tuple(sd["tfgridnet.embed_to_feats_proj.0.weight"].shape) == (6208, 256)

@@ -1,0 +1,206 @@
+"""Parity tests proper: the CUDA path, called through the reference-shaped API (which goes through
+the C ABI), against the CPU oracle and the committed fixtures.  fp32 gates (BASELINE.json):
+rel-L2 <= 1e-3 and |dSI-SDR| <= 0.1 dB."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lookoncetohear_b200 import Net, synth
+from oracle import restate as rs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_L2 = 1e-3
+SISDR_DB = 0.1
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def model(tsh_params, dev):
+    torch.manual_seed(0)
+    net = Net(**tsh_params).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net.to(dev), sd
+
+
+def _check(y, y_ref, tgt=None):
+    y = y.float().cpu()
+    assert y.shape == y_ref.shape
+    assert torch.isfinite(y).all()
+    err = rs.rel_l2(y, y_ref)
+    assert err <= REL_L2, f"rel-L2 {err:.3e}"
+    if tgt is not None:
+        d = (rs.si_sdr(y, tgt) - rs.si_sdr(y_ref, tgt)).abs().max()
+        assert float(d) <= SISDR_DB, f"dSI-SDR {float(d):.4f} dB"
+
+
+def test_native_library_is_loaded(model):
+    from lookoncetohear_b200 import _cabi
+    maps = open("/proc/self/maps").read()
+    assert "liblookonce_b200.so" in maps and _cabi.lib() is not None
+
+
+@pytest.mark.parametrize("B,N", [(1, 128 * 6), (2, 128 * 14 - 51), (3, 200), (1, 128)])
+def test_whole_utterance_vs_oracle(model, dev, B, N):
+    net, sd = model
+    x, tgt = synth.mixture(B, N, seed0=1000 + N)
+    e = synth.embedding(B)
+    y_ref = rs.sep_forward(sd, x, e)
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev))
+    _check(y, y_ref, tgt)
+
+
+def test_every_stage_vs_oracle(model, dev):
+    net, sd = model
+    x, _ = synth.mixture(2, 128 * 5 + 9)
+    e = synth.embedding(2)
+    taps_ref = {}
+    rs.sep_predict(sd, x, e[:, 0], rs.sep_init_state(sd, 2), taps=taps_ref)
+    with torch.no_grad():
+        _, taps, _ = net.forward_with_taps(x.to(dev), e.to(dev))
+    ref = [taps_ref["enc"]] + [taps_ref[f"block{b}{s}"] for b in range(3) for s in ("_intra", "_inter", "")]
+    ref[3] = ref[3] * taps_ref["gate"]      # gate folded into block 0's epilogue
+    for i, (t, r) in enumerate(zip(taps, ref)):
+        assert rs.rel_l2(t.cpu(), r) < 2e-4, f"stage {i}"
+
+
+def test_golden_fixture(model, dev, tsh_params):
+    g = np.load(os.path.join(GOLD, "sep_golden.npz"))
+    net, _ = model                                 # seed 0 == fixture seed
+    assert int(g["seed"]) == 0
+    B, N = int(g["B"]), int(g["N"])
+    x, tgt = synth.mixture(B, N)
+    e = synth.embedding(B)
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev))
+    _check(y, torch.from_numpy(g["y"]), tgt)
+
+
+def test_golden_fixture_long(model, dev):
+    """T = 70 frames > the 50-frame attention window (history wrap inside one call)."""
+    g = np.load(os.path.join(GOLD, "sep_golden_long.npz"))
+    net, _ = model
+    x, _ = synth.mixture(1, int(g["N"]), seed0=1100)
+    e = synth.embedding(1, seed0=3100)
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev)).cpu()
+    assert rs.rel_l2(y[..., -1024:], torch.from_numpy(g["y_tail"])) <= REL_L2
+    assert abs(float(y.pow(2).mean().sqrt()) / float(g["y_rms"]) - 1) < 1e-3
+
+
+@pytest.mark.parametrize("cpc", [1, 2, 5])
+def test_streaming_chunks_vs_whole_and_state(model, dev, cpc):
+    """The streaming-buffer API (init_buffers / predict(pad=False)) with 1, 2, 5 chunks per call:
+    output equals the whole-utterance oracle, and the final state equals the oracle's state
+    (the ring slot rotation is undone by SepState.to_reference)."""
+    net, sd = model
+    T, B = 60, 2                                    # 60 frames: ring wraps (> 50)
+    x, tgt = synth.mixture(B, 128 * T, seed0=77)
+    e = synth.embedding(B, seed0=78)
+    st_ref = rs.sep_init_state(sd, B)
+    y_ref, st_ref = rs.sep_predict(sd, x, e[:, 0], st_ref)
+    xp = F.pad(x, (0, 64)).to(dev)
+    ed = e[:, 0].to(dev)
+    st = net.init_buffers(B, dev)
+    outs = []
+    with torch.no_grad():
+        for i in range(0, T, cpc):
+            o, st = net.predict(xp[..., 128 * i:128 * (i + cpc) + 64], ed, st, pad=False)
+            outs.append(o)
+    _check(torch.cat(outs, -1), y_ref, tgt)
+    assert st.header() == (T, T // cpc)
+    got = st.to_reference()
+    for k in ("conv_buf", "deconv_buf", "istft_buf"):
+        assert rs.rel_l2(got[k].cpu(), st_ref[k]) < REL_L2, k
+    for i in range(3):
+        for k in ("K_buf", "V_buf", "h0", "c0"):
+            assert rs.rel_l2(got["gridnet_bufs"][f"buf{i}"][k].cpu(), st_ref["gridnet_bufs"][f"buf{i}"][k]) < REL_L2, (i, k)
+
+
+def test_mixed_call_sizes_and_embedding_change(model, dev):
+    """Calls of different sizes interleaved (3 frames, 1, 1, 7, ...), and the speaker embedding
+    changed mid-stream (the device-side gate memo must notice)."""
+    net, sd = model
+    sizes = [3, 1, 1, 7, 2, 1, 5]
+    T = sum(sizes)
+    x, _ = synth.mixture(1, 128 * T, seed0=5)
+    e1, e2 = synth.embedding(1, seed0=6)[:, 0], synth.embedding(1, seed0=7)[:, 0]
+    xp = F.pad(x, (0, 64))
+    st_ref = rs.sep_init_state(sd, 1)
+    st = net.init_buffers(1, dev)
+    t0, ref, got = 0, [], []
+    with torch.no_grad():
+        for i, n in enumerate(sizes):
+            e = e1 if i < 4 else e2
+            seg = xp[..., 128 * t0:128 * (t0 + n) + 64]
+            r, st_ref = rs.sep_predict(sd, seg, e, st_ref, pad=False)
+            o, st = net.predict(seg.to(dev), e.to(dev), st, pad=False)
+            ref.append(r)
+            got.append(o)
+            t0 += n
+    _check(torch.cat(got, -1), torch.cat(ref, -1))
+
+
+def test_linearity_of_front_and_back_is_not_assumed_but_silence_is_exact(model, dev):
+    """Size-independent property usable at full size: an all-zero mixture gives the same output
+    as the oracle's (bias-only path), and it is independent of the batch position."""
+    net, sd = model
+    x = torch.zeros(2, 2, 128 * 4)
+    e = synth.embedding(2)
+    e[1] = e[0]
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev)).cpu()
+    assert torch.equal(y[0], y[1])
+    _check(y, rs.sep_forward(sd, x, e))
+
+
+def test_full_size_clip_streaming_equals_whole(model, dev):
+    """BASELINE config sizes (4 s clip, T = 500): chunked streaming == one whole-utterance call,
+    and both match the oracle run on the same clip."""
+    net, sd = model
+    x, tgt = synth.mixture(1, 64000)
+    e = synth.embedding(1)
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev))
+        st = net.init_buffers(1, dev)
+        xp = F.pad(x, (0, 64)).to(dev)
+        ed = e[:, 0].to(dev)
+        ys = torch.cat([net.predict(xp[..., 128 * i:128 * i + 192], ed, st, pad=False)[0] for i in range(500)], -1)
+    assert rs.rel_l2(ys.cpu(), y.cpu()) < 1e-4
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    _check(y, rs.sep_forward(sd, x, e), tgt)
+
+
+def test_batch_split_path(model, dev):
+    """forward() splits large batches into independent launches (workspace bound)."""
+    net, sd = model
+    old = net.max_frames_per_launch
+    net.max_frames_per_launch = 8
+    try:
+        x, _ = synth.mixture(5, 128 * 4)
+        e = synth.embedding(5)
+        with torch.no_grad():
+            y = net(x.to(dev), e.to(dev))
+        _check(y, rs.sep_forward(sd, x, e))
+    finally:
+        net.max_frames_per_launch = old
+
+
+def test_host_streaming_entry_point(model, dev):
+    """l2h_sep_stream_host: pinned host buffers in, pinned host buffers out."""
+    net, sd = model
+    x, _ = synth.mixture(1, 128 * 20)
+    e = synth.embedding(1)
+    y_ref = rs.sep_forward(sd, x, e)
+    for cpc in (1, 4):
+        y = net.stream_host(x, e[:, 0].to(dev), chunks_per_call=cpc)
+        _check(y, y_ref)
