@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: separated frames/s (8 ms hops of a 16 kHz
+binaural stream) and the real-time factor, for BASELINE.json configs[1]: streaming separation,
+8 ms chunks, batch 1, fp32, one stream per GPU.
+
+A *step* = one pass of the hot path over one synthetic 4 s binaural mixture (500 hops) per GPU,
+fed chunk by chunk through the streaming-state API with a fresh state (state init is inside the
+step).  `value` = hops/s over all ranks with the clip resident in HBM (l2h_sep_stream_dev);
+`e2e` = the same through the C-ABI host-buffer call (l2h_sep_stream_host): every chunk is copied
+host->device from pinned memory and its 128 output samples per ear copied back, inside the timed
+region.  `--impl reference` times the reference's own CPU path (the reference modules when the
+checkout is present, else the oracle port) on the host cores with the same workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks-per-call C] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CLIP_SAMPLES = 64000          # 4 s @ 16 kHz (configs[0]/[1]: "single 4 s binaural mixture")
+HOP = 128
+FRAMES = CLIP_SAMPLES // HOP  # 500
+METRIC = "separated frames/sec (8 ms chunks, 16 kHz binaural, streaming, batch 1 per GPU)"
+# algorithmic work per hop per stream
+FLOP_PER_FRAME = 74.67e6
+BYTES_PER_FRAME = 5.50e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def time_cpu_streaming(frames, chunks_per_call, passes, threads, seed=0):
+    """The CPU path on the host cores: chunked predict(pad=False) over `frames` hops, B=1.
+    Uses the reference's own modules when the checkout exists, else the oracle port."""
+    from lookoncetohear_b200 import Net, synth
+    from lookoncetohear_b200.configs import TSH_PARAMS
+    from oracle import ref_loader, restate
+    torch.set_num_threads(threads)
+    x, _ = synth.mixture(1, frames * HOP)
+    e = synth.embedding(1)[:, 0]
+    xp = torch.nn.functional.pad(x, (0, 64))
+    step = HOP * chunks_per_call
+    if ref_loader.available():
+        kind = "reference"
+        net = ref_loader.reference_net(seed)
+
+        def one_pass():
+            st = net.init_buffers(1, "cpu")
+            for i in range(0, frames, chunks_per_call):
+                net.predict(xp[..., HOP * i:HOP * i + step + 64], e, st, pad=False)
+    else:
+        kind = "port"
+        restate.set_fast(True)            # ATen's fused LSTM, like the reference's nn.LSTM
+        torch.manual_seed(seed)
+        sd = {k: v.detach().clone() for k, v in Net(**TSH_PARAMS).state_dict().items()}
+
+        def one_pass():
+            st = restate.sep_init_state(sd, 1)
+            for i in range(0, frames, chunks_per_call):
+                restate.sep_predict(sd, xp[..., HOP * i:HOP * i + step + 64], e, st, pad=False)
+    best = None
+    with torch.no_grad():
+        for _ in range(passes):
+            t0 = time.perf_counter()
+            one_pass()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return frames / best, kind, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # each step = a bounded sample of the workload: 125 hops (1 s of audio) of the same clip, chunked.
+    # Chunk-by-chunk streaming on CPU is dispatch-bound and often fastest on ONE thread (SURVEY.md
+    # section 6), so probe 1 thread vs all cores first and run the timed steps on the faster setting.
+    sample_frames = 125
+    allc = os.cpu_count() or 1
+    probe = {t: time_cpu_streaming(25, args.chunks_per_call, 1, t)[0] for t in sorted({1, allc})}
+    threads = max(probe, key=probe.get)
+    times = []
+    kind = None
+    for i in range(args.warmup + args.steps):
+        fps, kind, dt = time_cpu_streaming(sample_frames, args.chunks_per_call, 1, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample_frames * len(times) / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf": value / 125.0,
+        "config": {"workload": "streaming separation, 8 ms chunks, batch=1, fp32 (BASELINE configs[1])",
+                   "chunks_per_call": args.chunks_per_call, "clip_s": 4.0, "sample": f"{sample_frames} hops per step"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{sample_frames} hops of the 4 s clip per step, chunked predict(pad=False), "
+                                   f"{cpu_model_name()}"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks-per-call", type=int, default=1,
+                    help="hops handed to the engine per call (1 = true chunk-by-chunk streaming)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the latency / buffered-throughput extras")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from lookoncetohear_b200 import Net, _cabi, build, synth
+    from lookoncetohear_b200.configs import TSH_PARAMS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- weights: rank 0 owns them, NCCL broadcast to the other ranks ---------------------------
+    torch.manual_seed(0 if rank == 0 else 12345 + rank)      # non-zero ranks start with different values
+    net = Net(**TSH_PARAMS).eval().to(dev)
+    emb = synth.embedding(1, seed0=3000)[:, 0].to(dev)
+    if world > 1:
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, src=0)
+        dist.broadcast(emb, src=0)
+        net.refresh_weights()
+
+    cpc = args.chunks_per_call
+    n_calls = (FRAMES + cpc - 1) // cpc
+    x_cpu, _ = synth.mixture(1, CLIP_SAMPLES, seed0=1000 + rank)
+    x_dev = x_cpu.to(dev)
+    x_pin = x_cpu.pin_memory()
+    y_dev = torch.empty(1, 2, CLIP_SAMPLES, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)      # 256 MiB > 126 MB L2
+    L = _cabi.lib()
+
+    def step_dev():
+        st = net.init_buffers(1, dev)
+        net.stream_dev(x_dev, emb, chunks_per_call=cpc, state=st, n_calls=n_calls, out=y_dev)
+
+    def step_host():
+        return net.stream_host(x_pin, emb, chunks_per_call=cpc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1.0)                                         # L2 flush between timed iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_dev()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- end-to-end arm (host buffers, H2D/D2H inside) -----------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        y_host = step_host()
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)          # the call ends with a stream sync; take the larger
+    clocks = sampler.result()
+
+    tm = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(tm[0]), float(tm[1])
+    frames_total = world * FRAMES * args.steps
+    value = frames_total / (dev_ms * 1e-3)
+    e2e_value = frames_total / (e2e_ms * 1e-3)
+
+    nl = ctypes.c_int32()
+    _cabi.check(L.l2h_sep_launches_per_forward(net._engine(), cpc, ctypes.byref(nl)))
+    launches_per_step = 2 + n_calls * nl.value                   # state init + clip base + chains
+
+    extras = {}
+    roof = None
+    cpu_base = None
+    if rank == 0 and not args.no_extras:
+        # single-chunk latency: one call, synchronised, median of 200 (graph replay)
+        st = net.init_buffers(1, dev)
+        lat = []
+        net.stream_dev(x_dev, emb, chunks_per_call=1, state=st, n_calls=60, out=y_dev)
+        torch.cuda.synchronize()
+        for i in range(200):
+            t0 = time.perf_counter()
+            net.stream_dev(x_dev[..., :HOP * 8], emb, chunks_per_call=1, state=st, n_calls=1, out=y_dev[..., :HOP * 8])
+            torch.cuda.synchronize()
+            lat.append(time.perf_counter() - t0)
+        extras["chunk_latency_us"] = 1e6 * statistics.median(lat)
+        # buffered throughput: more hops per call (latency traded for throughput), same clip, same state API
+        buf = {}
+        for c in (4, 20, 500):
+            nc = (FRAMES + c - 1) // c
+            for it in range(3):
+                st = net.init_buffers(1, dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                net.stream_dev(x_dev, emb, chunks_per_call=c, state=st, n_calls=nc, out=y_dev)
+                b.record()
+                torch.cuda.synchronize()
+                buf[str(c)] = FRAMES / (a.elapsed_time(b) * 1e-3)
+        extras["frames_per_s_by_chunks_per_call"] = buf
+    if rank == 0:
+        # per-kernel device times of one streaming chain (CUDA events on the launching stream)
+        prof = profile_chain(net, x_dev, emb, dev, cpc)
+        pk = peaks()
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms_total"])
+        # dominant kernel: algorithmic bytes per launch / its mean duration
+        alg = kernel_algorithmic_bytes(dom[0], cpc)
+        ach = alg / (dom[1]["ms_mean"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "alg_bytes_per_launch": alg, "mean_us_per_launch": 1e3 * dom[1]["ms_mean"],
+                "share_of_chain": dom[1]["ms_total"] / sum(v["ms_total"] for v in prof.values()),
+                "note": "batch-1 streaming is latency-bound (serial LSTM chain, 13 MB working set resident in L2); "
+                        "whole-chain algorithmic rate: %.1f GB/s, %.2f TFLOP/s fp32" % (
+                            value / world * BYTES_PER_FRAME / 1e9, value / world * FLOP_PER_FRAME / 1e12)}
+        extras["kernel_us"] = {k: round(1e3 * v["ms_mean"], 2) for k, v in prof.items()}
+        if world == 1:
+            allc = os.cpu_count() or 1
+            res = {t: time_cpu_streaming(125, cpc, 2, t) for t in sorted({1, allc})}
+            threads = max(res, key=lambda t: res[t][0])
+            cpu_base = {"value": res[threads][0], "unit": "frames/s", "cores": threads, "kind": res[threads][1],
+                        "sample": "125 hops (1 s) of the same clip, chunked predict(pad=False), best of 2; "
+                                  f"{cpu_model_name()}; host has {allc} cores",
+                        "by_threads": {str(t): r[0] for t, r in res.items()}}
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": value / world / 125.0,
+            "config": {"workload": "streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); "
+                                   "4 s clip = 500 hops per step, fresh state per step",
+                       "chunks_per_call": cpc, "parallelism": f"dp{world} (independent streams, weights broadcast over NCCL)",
+                       "l2": "flushed (256 MiB write) between timed iterations"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_calls * 2 * (HOP * cpc + 64) * 4,
+                    "d2h_bytes_per_step": n_calls * 2 * HOP * cpc * 4, "rtf": e2e_value / world / 125.0,
+                    "api": "l2h_sep_stream_host (pinned host buffers, per-chunk cudaMemcpyAsync in the timed region)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "wall_s": t_wall,
+        }
+        out.update(extras)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_algorithmic_bytes(name, cpc):
+    """Algorithmic HBM bytes of one launch of a chain kernel at batch 1."""
+    rows = 97 * cpc
+    if name == "lstm_intra":
+        return rows * 512 * 4 + rows * 128 * 4 + 2 * 256 * 64 * 4
+    if name == "lstm_inter":
+        return rows * 256 * 4 + rows * 64 * 4 + 256 * 64 * 4 + 2 * 2 * 97 * 64 * 4
+    if name == "attn":
+        return cpc * 4 * (584 * 4 + 50 * (584 + 1552) * 4 + 1552 * 4) if cpc == 1 else \
+            4 * ((49 + cpc) * (584 + 1552) * 4 + cpc * (584 + 1552) * 4)
+    return rows * 64 * 4 * 2
+
+
+def profile_chain(net, x_dev, emb, dev, cpc, iters=20):
+    """Times every kernel of the chain with CUDA events (l2h_sep_profile) -> {name: {ms_mean, ms_total}}."""
+    from lookoncetohear_b200 import _cabi
+    L = _cabi.lib()
+    st = net.init_buffers(1, dev)
+    ws, _ = net._workspace(dev, 1, cpc)
+    n = ctypes.c_int32()
+    names = (ctypes.c_char_p * 64)()
+    ms = (ctypes.c_float * 64)()
+    cnt = (ctypes.c_int32 * 64)()
+    y = torch.empty(1, 2, HOP * cpc, device=dev)
+    x = x_dev[..., :HOP * cpc + 64].contiguous()
+    with torch.cuda.device(dev):
+        _cabi.check(L.l2h_sep_profile(net._engine(), x.data_ptr(), x.shape[-1], emb.data_ptr(), st.buf.data_ptr(),
+                                      y.data_ptr(), 1, cpc, ws.data_ptr(), ws.numel(), iters, names, ms, cnt,
+                                      ctypes.byref(n), torch.cuda.current_stream(dev).cuda_stream))
+    out = {}
+    for i in range(n.value):
+        out[names[i].decode()] = {"ms_total": ms[i] / iters, "ms_mean": ms[i] / max(1, cnt[i])}
+    return out
+
+
+if __name__ == "__main__":
+    main()

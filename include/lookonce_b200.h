@@ -57,7 +57,9 @@ typedef struct l2h_sep_config {
 } l2h_sep_config;
 
 /* flags for l2h_sep_forward */
-#define L2H_FLAG_TAPS 1u /* also copy the activations after every stage into the tap area */
+#define L2H_FLAG_TAPS 1u  /* also copy the activations after every stage into the tap area */
+#define L2H_FLAG_GRAPH 2u /* replay the kernel chain from a CUDA graph cached on the exact argument set
+                             (pointers, strides, sizes): for callers that reuse fixed staging buffers */
 
 int l2h_abi_version(void);
 const char* l2h_last_error(void);
@@ -104,10 +106,26 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
                         float* y_stage_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
 
+/* Streaming with DEVICE buffers: x_dev [batch][num_ch][x_len] holds whole clips, y_dev
+ * [batch][num_src][y_len]; n_calls chained calls of chunks_per_call frames each, starting at the
+ * beginning of x_dev and continuing the state.  Each call is one CUDA-graph replay; the chunk a
+ * replay works on is derived on the device from the state's frame counter.  Asynchronous. */
+int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const float* emb_dev,
+                       void* state_dev, float* y_dev, int32_t y_len, int32_t batch, int32_t n_calls,
+                       int32_t chunks_per_call, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* where the tap area starts inside the workspace (floats) and its stage count; stage s holds
  * [batch*frames*97*64] floats: 0 = encoder out, then per block: after intra, after inter, block out */
 int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* offset_floats,
                      int32_t* n_stages);
+
+/* Measurement aid: run the chain `iters` times (after 2 warm-ups) with a CUDA event between every
+ * launch on `stream`; returns, per kernel name (<= 64), the summed device time in ms and the launch
+ * count.  Advances the state by (iters+2)*frames.  Synchronises. */
+int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float* emb_dev, void* state_dev,
+                    float* y_dev, int32_t batch, int32_t frames, void* workspace_dev, size_t workspace_bytes,
+                    int32_t iters, const char** names, float* ms_total, int32_t* counts, int32_t* n_names,
+                    void* stream);
 
 /* number of kernels one l2h_sep_forward launches (for bench.py's gpu_launches) */
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);

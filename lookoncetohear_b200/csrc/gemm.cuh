@@ -167,16 +167,24 @@ rows_gemm_kernel(const GemmArgs g) {
 }
 
 template <int BM, int BN, int TM, int TN>
+inline cudaError_t configure_rows_gemm_cfg() {
+    const size_t smem = (size_t)(GK * (BM + 4) + GK * BN) * sizeof(float);
+    return cudaFuncSetAttribute(rows_gemm_kernel<BM, BN, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem);
+}
+
+// call once per process before the first launch (and outside stream capture)
+inline cudaError_t configure_rows_gemm() {
+    cudaError_t e = configure_rows_gemm_cfg<16, 64, 2, 4>();
+    if (e == cudaSuccess) e = configure_rows_gemm_cfg<64, 128, 4, 8>();
+    if (e == cudaSuccess) e = configure_rows_gemm_cfg<64, 64, 4, 4>();
+    return e;
+}
+
+template <int BM, int BN, int TM, int TN>
 inline cudaError_t launch_rows_gemm_cfg(const GemmArgs& g, cudaStream_t st) {
     constexpr int NT = (BM / TM) * (BN / TN);
     const size_t smem = (size_t)(GK * (BM + 4) + GK * BN) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rows_gemm_kernel<BM, BN, TM, TN>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     dim3 grid((g.M + BM - 1) / BM, g.N / BN);
     rows_gemm_kernel<BM, BN, TM, TN><<<grid, NT, smem, st>>>(g);
     return cudaGetLastError();

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -50,6 +51,10 @@ struct SepEngine {
     SepWeights w;
     std::vector<BlockWeights> bw;
     bool committed = false;
+    // CUDA-graph cache of whole kernel chains (the T=1 streaming chain is ~30 tiny kernels:
+    // launch-bound unless replayed as a graph)
+    std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
+    cudaStream_t cap_stream = nullptr;
 };
 
 static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
@@ -217,13 +222,36 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
+    CK(configure_rows_gemm());
     g_attr_done = true;
     return 0;
 }
 
-static int sep_forward_impl(SepEngine* e, const float* x, int64_t xbs, int64_t xcs, int x_len, const float* emb,
-                            float* state, float* y, int64_t ybs, int64_t ycs, int y_len, int B, int T,
-                            float* wsp, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+struct Profiler {                      // per-kernel device times via CUDA events on the launching stream
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    int used = 0;
+    int mark(const char* name, cudaStream_t st) {
+        if (used == (int)ev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); ev.push_back(e); }
+        CK(cudaEventRecord(ev[used++], st));
+        names.push_back(name);
+        return 0;
+    }
+};
+
+struct ChainArgs {
+    const float* x; int64_t xbs, xcs; int x_len;
+    const float* emb; float* state;
+    float* y; int64_t ybs, ycs; int y_len;
+    int B, T; float* wsp; size_t ws_bytes; uint32_t flags; int pos_rel;
+    Profiler* prof = nullptr;
+};
+
+static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
+    const float* x = a.x; const int64_t xbs = a.xbs, xcs = a.xcs; const int x_len = a.x_len;
+    const float* emb = a.emb; float* state = a.state; float* y = a.y;
+    const int64_t ybs = a.ybs, ycs = a.ycs; const int y_len = a.y_len, B = a.B, T = a.T;
+    float* wsp = a.wsp; const size_t ws_bytes = a.ws_bytes; const uint32_t flags = a.flags;
     if (!e->committed) return fail(4, "weights not committed");
     if (B <= 0 || T <= 0) return fail(1, "batch and frames must be positive");
     const Workspace ws = carve(e->n_blocks, B, T, flags);
@@ -244,13 +272,17 @@ static int sep_forward_impl(SepEngine* e, const float* x, int64_t xbs, int64_t x
         return 0;
     };
     float* sbase = state + sizeof(StateHeader) / 4;
-
-    front_kernel<<<dim3(T, B), 256, 0, st>>>(x, xbs, xcs, x_len, X, state, ss, e->w, T);
+#define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
+    MARK("start");
+    front_kernel<<<dim3(T, B), 256, 0, st>>>(x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel);
     CK(cudaGetLastError());
+    MARK("front");
     spk_gemv_kernel<<<dim3(FC / 32, B), 256, 0, st>>>(emb, PRE, state, ss, e->w);
     CK(cudaGetLastError());
+    MARK("spk_gemv");
     spk_ln_kernel<<<B, 256, 0, st>>>(emb, PRE, state, ss, e->w);
     CK(cudaGetLastError());
+    MARK("spk_ln");
     if (int rc = do_tap()) return rc;
 
     for (int b = 0; b < e->n_blocks; ++b) {
@@ -260,21 +292,25 @@ static int sep_forward_impl(SepEngine* e, const float* x, int64_t xbs, int64_t x
         g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
         g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
         CK(launch_rows_gemm(g, st));
+        MARK("gemm_ih_intra");
         LstmArgs l{};
         l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
         l.nseq = B * T; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1;
         l.ndir = 2;
         CK(launch_lstm_rec(l, st));
+        MARK("lstm_intra");
         g = GemmArgs{};
         g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
         g.M = (int)rows; g.N = 64; g.K = 128;
         CK(launch_rows_gemm(g, st));
+        MARK("gemm_lin_intra");
         if (int rc = do_tap()) return rc;
         // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
         g = GemmArgs{};
         g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
         g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
         CK(launch_rows_gemm(g, st));
+        MARK("gemm_ih_inter");
         l = LstmArgs{};
         l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
         l.h_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
@@ -283,26 +319,64 @@ static int sep_forward_impl(SepEngine* e, const float* x, int64_t xbs, int64_t x
         l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
         l.step_stride = NF; l.ndir = 1;
         CK(launch_lstm_rec(l, st));
+        MARK("lstm_inter");
         g = GemmArgs{};
         g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
         g.M = (int)rows; g.N = 64; g.K = 64;
         CK(launch_rows_gemm(g, st));
+        MARK("gemm_lin_inter");
         if (int rc = do_tap()) return rc;
         // ---- attention --------------------------------------------------------------------------
         if (T > 1) {
             kv_gather_kernel<<<dim3(ATT - 1, B * NHEAD), 128, 0, st>>>(state, ss, b, KALL, VALL, T);
             CK(cudaGetLastError());
+            MARK("kv_gather");
         }
         qkv_kernel<<<dim3(T, B), QKV_THREADS, QKV_SMEM, st>>>(X, Q, KALL, VALL, state, ss, b, W, T);
         CK(cudaGetLastError());
+        MARK("qkv");
         attn_kernel<<<dim3(T, NHEAD, B), 256, 0, st>>>(Q, KALL, VALL, state, ss, b, Z, T);
         CK(cudaGetLastError());
+        MARK("attn");
         attn_out_kernel<<<dim3(T, B), 256, AOUT_SMEM, st>>>(Z, X, state, ss, W, (b == 0 && e->n_blocks > 1) ? 1 : 0, T);
         CK(cudaGetLastError());
+        MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
-    back_kernel<<<dim3(T, B), 256, BACK_SMEM, st>>>(X, y, ybs, ycs, y_len, state, ss, e->w, T);
+    back_kernel<<<dim3(T, B), 256, BACK_SMEM, st>>>(X, y, ybs, ycs, y_len, state, ss, e->w, T, a.pos_rel);
     CK(cudaGetLastError());
+    MARK("back");
+#undef MARK
+    return 0;
+}
+
+// Launch the chain directly, or replay it from a cached CUDA graph (captured on a private
+// stream the first time this exact argument set is seen; graph launches go to the caller's stream).
+static int run_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st, bool use_graph) {
+    if (!use_graph || (a.flags & L2H_FLAG_TAPS)) return enqueue_chain(e, a, st);
+    std::vector<int64_t> key = {(int64_t)a.x, a.xbs, a.xcs, a.x_len, (int64_t)a.emb, (int64_t)a.state, (int64_t)a.y,
+                                a.ybs, a.ycs, a.y_len, a.B, a.T, (int64_t)a.wsp, (int64_t)a.flags, a.pos_rel};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        if (!e->committed) return fail(4, "weights not committed");
+        if (int rc = set_attrs()) return rc;
+        if (!e->cap_stream) CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+        if (e->graphs.size() >= 32) {
+            for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+            e->graphs.clear();
+        }
+        CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_chain(e, a, e->cap_stream);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(3, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = e->graphs.emplace(key, exec).first;
+    }
+    CK(cudaGraphLaunch(it->second, st));
     return 0;
 }
 
@@ -333,6 +407,8 @@ int l2h_sep_create(const l2h_sep_config* c, void** handle) {
 int l2h_sep_destroy(void* handle) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e) return 0;
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     if (e->dev) cudaFree(e->dev);
     delete e;
     return 0;
@@ -433,8 +509,9 @@ int l2h_sep_forward(void* handle, const float* x, int64_t xbs, int64_t xcs, int3
                     void* ws, size_t ws_bytes, uint32_t flags, void* stream) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !x || !emb || !state || !y || !ws) return fail(1, "null argument");
-    return sep_forward_impl(e, x, xbs, xcs, x_len, emb, static_cast<float*>(state), y, ybs, ycs, y_len, batch,
-                            frames, static_cast<float*>(ws), ws_bytes, flags, static_cast<cudaStream_t>(stream));
+    ChainArgs a{x, xbs, xcs, x_len, emb, static_cast<float*>(state), y, ybs, ycs, y_len, batch, frames,
+                static_cast<float*>(ws), ws_bytes, flags & ~L2H_FLAG_GRAPH, 0};
+    return run_chain(e, a, static_cast<cudaStream_t>(stream), (flags & L2H_FLAG_GRAPH) != 0);
 }
 
 int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const float* emb, void* state,
@@ -451,9 +528,10 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
         if (n_in <= 0) return fail(1, "x_host shorter than n_calls * chunks_per_call * 128 samples");
         CK(cudaMemcpy2DAsync(x_stage, in_len * sizeof(float), x_host + s0, (size_t)x_len * sizeof(float),
                              (size_t)n_in * sizeof(float), (size_t)batch * NMIC, cudaMemcpyHostToDevice, st));
-        int rc = sep_forward_impl(e, x_stage, (int64_t)NMIC * in_len, in_len, n_in, emb, static_cast<float*>(state),
-                                  y_stage, (int64_t)NSRC * out_len, out_len, out_len, batch, cpc,
-                                  static_cast<float*>(ws), ws_bytes, 0, st);
+        // (a short last chunk changes x_len and therefore the graph key: at most two graphs)
+        ChainArgs a{x_stage, (int64_t)NMIC * in_len, in_len, n_in, emb, static_cast<float*>(state), y_stage,
+                    (int64_t)NSRC * out_len, out_len, out_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 0};
+        int rc = run_chain(e, a, st, true);
         if (rc) return rc;
         int n_out = y_len - s0;
         if (n_out > out_len) n_out = out_len;
@@ -462,6 +540,66 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
                                  (size_t)n_out * sizeof(float), (size_t)batch * NSRC, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const float* emb, void* state,
+                       float* y_dev, int32_t y_len, int32_t batch, int32_t n_calls, int32_t cpc, void* ws,
+                       size_t ws_bytes, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !x_dev || !emb || !state || !y_dev || !ws) return fail(1, "null argument");
+    if (n_calls <= 0 || cpc <= 0) return fail(1, "n_calls and chunks_per_call must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    set_clip_base_kernel<<<1, 1, 0, st>>>(static_cast<float*>(state));
+    CK(cudaGetLastError());
+    ChainArgs a{x_dev, (int64_t)NMIC * x_len, x_len, x_len, emb, static_cast<float*>(state), y_dev,
+                (int64_t)NSRC * y_len, y_len, y_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 1};
+    for (int i = 0; i < n_calls; ++i)
+        if (int rc = run_chain(e, a, st, true)) return rc;
+    return 0;
+}
+
+int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float* emb, void* state, float* y_dev,
+                    int32_t batch, int32_t frames, void* ws, size_t ws_bytes, int32_t iters, const char** names,
+                    float* ms_total, int32_t* counts, int32_t* n_names, void* stream) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !x_dev || !emb || !state || !y_dev || !ws || !names || !ms_total || !counts || !n_names)
+        return fail(1, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Profiler prof;
+    std::vector<std::string> order;
+    std::map<std::string, std::pair<double, int>> acc;
+    const int out_len = HOP * frames;
+    for (int it = -2; it < iters; ++it) {           // two untimed warm-up chains
+        prof.used = 0;
+        prof.names.clear();
+        ChainArgs a{x_dev, (int64_t)NMIC * x_len, x_len, x_len, emb, static_cast<float*>(state), y_dev,
+                    (int64_t)NSRC * out_len, out_len, out_len, batch, frames, static_cast<float*>(ws), ws_bytes, 0, 0};
+        a.prof = &prof;
+        if (int rc = enqueue_chain(e, a, st)) return rc;
+        CK(cudaStreamSynchronize(st));
+        if (it < 0) continue;
+        for (int i = 1; i < prof.used; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, prof.ev[i - 1], prof.ev[i]));
+            const std::string nm = prof.names[i];
+            if (!acc.count(nm)) order.push_back(nm);
+            acc[nm].first += ms;
+            acc[nm].second += 1;
+        }
+    }
+    for (auto ev : prof.ev) cudaEventDestroy(ev);
+    static std::vector<std::string> keep;            // storage for the returned C strings
+    keep = order;
+    int n = 0;
+    for (auto& nm : keep) {
+        if (n >= 64) break;
+        names[n] = nm.c_str();
+        ms_total[n] = (float)acc[nm].first;
+        counts[n] = acc[nm].second;
+        ++n;
+    }
+    *n_names = n;
     return 0;
 }
 

@@ -59,13 +59,19 @@ __global__ void state_init_kernel(float* state, int64_t total_floats, int64_t st
     }
 }
 
+__global__ void set_clip_base_kernel(float* state) {
+    StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
+    hdr->clip_base = hdr->pos;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1 front: STFT analysis + channel regroup + causal 3x3 conv   (tfgridnet_causal.py:229-242)
 // grid (T, B), 256 threads.  x: [B][NMIC][x_len] (samples past x_len read as zero: the mod-pad and
 // look-ahead zeros of net.py:8-18,56-58).  Frames before the call start come from conv_buf.
 __global__ void __launch_bounds__(256)
 front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
-             float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T) {
+             float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T,
+             int pos_rel) {
     __shared__ float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -76,7 +82,8 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
 
     for (int i = tid; i < 3 * 4 * 100; i += 256) (&U[0][0][0])[i] = 0.f;
-    const int s0 = HOP * (t - 2);
+    // pos_rel: x is a whole clip and this call starts at frame (pos - clip_base) of it
+    const int s0 = HOP * (t - 2) + (pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0);
     for (int i = tid; i < NMIC * 448; i += 256) {
         const int m = i / 448, n = i % 448, s = s0 + n;
         xs[m][n] = (s >= 0 && s < x_len) ? x[(int64_t)b * x_bstride + (int64_t)m * x_cstride + s] : 0.f;
@@ -459,7 +466,7 @@ constexpr size_t BACK_SMEM = (size_t)(4 * 99 * 64 + 2 * NSRC * NROW + NSRC * HOP
 
 __global__ void __launch_bounds__(256)
 back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
-            int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T) {
+            int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel) {
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]
     float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
@@ -468,6 +475,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
+    const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* db = st + ST_DECONV + par * (2 * FC);
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
@@ -534,7 +542,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     __syncthreads();
     for (int i = tid; i < NSRC * HOP; i += 256) {
         const int ear = i / HOP, n = i % HOP;
-        const int s = HOP * t + n;
+        const int s = HOP * t + n + soff;
         if (s < y_len) {
             float v = outs[i];
             if (n < LOOKAHEAD) v += tails[ear * LOOKAHEAD + n];

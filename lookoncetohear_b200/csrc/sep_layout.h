@@ -28,12 +28,15 @@ constexpr int NQKV = 2 * NHEAD * QE + NHEAD * VD;  // 112
 
 // ---- state: one allocation = header + B stream records ---------------------------------------
 // header (64 B): int64 pos (frames consumed so far), int64 ncalls (parity for the small
-// double-buffered tails), int32 done (last-CTA counter of the final kernel).
+// double-buffered tails), int64 clip_base (pos at the start of the clip being streamed: lets a
+// captured CUDA graph address "chunk pos - clip_base" of a whole-clip buffer without any
+// per-launch parameter), int32 done (last-CTA counter of the final kernel).
 struct StateHeader {
     long long pos;
     long long ncalls;
+    long long clip_base;
     int done;
-    int pad[11];
+    int pad[9];
 };
 static_assert(sizeof(StateHeader) == 64, "header");
 

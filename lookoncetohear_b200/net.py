@@ -308,6 +308,31 @@ class Net(nn.Module):
             outs.append(self.predict(xs, es, st, pad)[0])
         return torch.cat(outs, dim=0)
 
+    def stream_dev(self, x_dev, embed_dev, chunks_per_call=1, state=None, n_calls=None, out=None):
+        """Streaming over a device-resident clip (l2h_sep_stream_dev): x_dev [B,M,N] is consumed
+        chunks_per_call hops per call with the state carried, every call one CUDA-graph replay.
+        Returns y [B,S,N] (device).  Asynchronous."""
+        self._require_cuda(x_dev)
+        dev = x_dev.device
+        self._sync_weights(dev)
+        hop = self.stft_chunk_size
+        x = x_dev.contiguous().float()
+        Bsz, _, n = x.shape
+        step = hop * chunks_per_call
+        if n_calls is None:
+            n_calls = (n + step - 1) // step
+        if state is None:
+            state = self.init_buffers(Bsz, dev)
+        y = out if out is not None else torch.empty(Bsz, self.num_src, n, dtype=torch.float32, device=dev)
+        ws, _ = self._workspace(dev, Bsz, chunks_per_call)
+        emb = embed_dev.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().l2h_sep_stream_dev(
+                self._engine(), x.data_ptr(), n, emb.data_ptr(), state.buf.data_ptr(), y.data_ptr(), n, Bsz,
+                n_calls, chunks_per_call, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        self._last_stream_state = state
+        return y
+
     def stream_host(self, x_host, embed_dev, chunks_per_call=1, state=None):
         """End-to-end streaming with HOST buffers (l2h_sep_stream_host): x_host [B,M,N] CPU tensor
         (pinned here if it is not), every call copies its chunk host->device, runs the chain and

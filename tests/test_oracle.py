@@ -97,6 +97,19 @@ def test_restatement_streaming_equals_whole(tsh_params):
     assert rs.rel_l2(ys, y) < 5e-6
 
 
+def test_fast_timing_mode_equals_explicit_loop(tsh_params):
+    sd = _seeded_sd(tsh_params, 6)
+    x, _ = synth.mixture(1, 128 * 5)
+    e = synth.embedding(1)
+    y = rs.sep_forward(sd, x, e)
+    rs.set_fast(True)
+    try:
+        yf = rs.sep_forward(sd, x, e)
+    finally:
+        rs.set_fast(False)
+    assert rs.rel_l2(yf, y) < 5e-6
+
+
 def test_golden_sep(tsh_params):
     g = np.load(os.path.join(GOLD, "sep_golden.npz"))
     sd = _seeded_sd(tsh_params, int(g["seed"]))
