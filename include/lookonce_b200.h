@@ -130,6 +130,30 @@ int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float
 /* number of kernels one l2h_sep_forward launches (for bench.py's gpu_launches) */
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);
 
+/* ---- enrollment network (EmbedTFGridNet, configs/embed.json:5-10) ---------------------------- */
+typedef struct l2h_embed_config {
+    int32_t embed_dim;  /* 256 */
+    int32_t num_ch;     /* 2   */
+    int32_t n_fft;      /* 128 */
+    int32_t stride;     /* 64  */
+    int32_t num_blocks; /* 3   */
+} l2h_embed_config;
+
+int l2h_embed_create(const l2h_embed_config* cfg, void** handle);
+int l2h_embed_destroy(void* handle);
+/* name = a key of the reference EmbedTFGridNet state_dict (espnet2 naming: "blocks.0.intra_norm.gamma",
+ * "blocks.0.attn_conv_Q_0.0.weight", "embed_proj.0.weight", ...); HOST fp32.  The unused deconv.* tensors
+ * are accepted and ignored. */
+int l2h_embed_load_weight(void* handle, const char* name, const float* host_data, int64_t numel);
+int l2h_embed_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loaded);
+int l2h_embed_commit_weights(void* handle, void* stream);
+int l2h_embed_workspace_bytes(void* handle, int32_t batch, int32_t n_samples, size_t* bytes);
+/* largest batch one l2h_embed_forward call should be given for utterances of n_samples (workspace bound) */
+int l2h_embed_max_batch(void* handle, int32_t n_samples, int32_t* max_batch);
+/* x_dev [batch][2][n_samples] fp32 contiguous -> emb_dev [batch][256].  Asynchronous on `stream`. */
+int l2h_embed_forward(void* handle, const float* x_dev, float* emb_dev, int32_t batch, int32_t n_samples,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ net), behind the reference's own Python call signatures.
 Compute happens only in lib/liblookonce_b200.so (hand-written sm_100a CUDA, C ABI declared in
 include/lookonce_b200.h); importing this package never falls back to PyTorch math.
 """
+from .embed import EmbedTFGridNet  # noqa: F401
 from .net import Net, SepState  # noqa: F401
 
-__all__ = ["Net", "SepState"]
+__all__ = ["Net", "SepState", "EmbedTFGridNet"]

@@ -20,6 +20,11 @@ class SepConfig(ctypes.Structure):
         "local_atten_len", "use_attn", "lookahead", "chunk_causal", "num_src")]
 
 
+class EmbedConfig(ctypes.Structure):
+    """l2h_embed_config (configs/embed.json model_params)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("embed_dim", "num_ch", "n_fft", "stride", "num_blocks")]
+
+
 _lib = None
 
 _SIGS = {
@@ -60,6 +65,17 @@ _SIGS = {
                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]),
     "l2h_sep_launches_per_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
                                                    ctypes.POINTER(ctypes.c_int32)]),
+    "l2h_embed_create": (ctypes.c_int, [ctypes.POINTER(EmbedConfig), c_void_pp]),
+    "l2h_embed_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "l2h_embed_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]),
+    "l2h_embed_weights_expected": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
+                                                 ctypes.POINTER(ctypes.c_int32)]),
+    "l2h_embed_commit_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "l2h_embed_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.POINTER(ctypes.c_size_t)]),
+    "l2h_embed_max_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "l2h_embed_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
 }
 
 

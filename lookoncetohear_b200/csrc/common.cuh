@@ -47,6 +47,13 @@ L2H_DEVINL float block_sum(float v, float* red) {
 L2H_DEVINL float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 L2H_DEVINL float fast_tanh(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
+// 2^x, flush-to-zero (plain ex2.approx carries extra denormal-range fix-up instructions)
+L2H_DEVINL float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 L2H_DEVINL float prelu(float x, float a) { return x >= 0.f ? x : a * x; }
 
 // cp.async 16 B (LDGSTS)
@@ -58,4 +65,30 @@ L2H_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 L2H_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor drains; griddep_wait() blocks until the predecessor
+// grid has completed and flushed.  Every kernel of a chain calls griddep_launch() first (lets the
+// successor's CTAs become resident early and run their weight-only prologue) and griddep_wait()
+// before touching anything an earlier kernel wrote -- on every path, so completion stays
+// transitive.  Both are no-ops for launches without the attribute.
+L2H_DEVINL void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+L2H_DEVINL void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace l2h
+
+#include <utility>
+namespace l2h {
+// host: launch with (or without) the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 }  // namespace l2h

@@ -22,12 +22,15 @@ struct GemmArgs {
     const float* bias;       // [N] or null
     float* C;
     int64_t ldc;
-    int c_rows_per_seq;      // 0 => plain
-    int64_t c_seq_stride;
+    int c_rows_per_seq;      // 0 => plain; else row m -> (seq = m / c_rows_per_seq, p = m % c_rows_per_seq)
+    int64_t c_seq_stride;    //   offset = (seq / c_inner)*c_seq_stride + (seq % c_inner)*c_inner_stride + p*ldc
+    int c_inner;             //   (c_inner <= 1 => offset = seq*c_seq_stride + p*ldc)
+    int64_t c_inner_stride;
     const float* R;          // residual, indexed like C (may alias C); null => none
     const float* ln_g;       // LN prologue (requires K == 64); null => none
     const float* ln_b;
     const float* prelu;      // scalar slope pointer; null => none
+    const float* prelu_vec;  // per-output-column slopes [N]; null => none
     int M, N, K;
 };
 
@@ -42,6 +45,7 @@ rows_gemm_kernel(const GemmArgs g) {
     float* As = smem;                      // [GK][BM + APAD]  (transposed: k-major)
     float* Bs = smem + GK * (BM + APAD);   // [GK][BN]
 
+    griddep_launch();
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
@@ -54,6 +58,7 @@ rows_gemm_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
+    griddep_wait();
     for (int k0 = 0; k0 < g.K; k0 += GK) {
         // ---- A tile: 16 lanes per row, one float4 each (64 floats / row) ------------------
         for (int r = tid / 16; r < BM; r += NT / 16) {
@@ -141,7 +146,11 @@ rows_gemm_kernel(const GemmArgs g) {
         int64_t coff;
         if (g.c_rows_per_seq > 0) {
             const int seq = m / g.c_rows_per_seq, p = m % g.c_rows_per_seq;
-            coff = (int64_t)seq * g.c_seq_stride + (int64_t)p * g.ldc;
+            if (g.c_inner > 1)
+                coff = (int64_t)(seq / g.c_inner) * g.c_seq_stride + (int64_t)(seq % g.c_inner) * g.c_inner_stride +
+                       (int64_t)p * g.ldc;
+            else
+                coff = (int64_t)seq * g.c_seq_stride + (int64_t)p * g.ldc;
         } else {
             coff = (int64_t)m * g.ldc;
         }
@@ -156,6 +165,11 @@ rows_gemm_kernel(const GemmArgs g) {
             if (g.prelu) {
                 o.x = prelu(o.x, slope); o.y = prelu(o.y, slope);
                 o.z = prelu(o.z, slope); o.w = prelu(o.w, slope);
+            }
+            if (g.prelu_vec) {
+                const float4 sv = *reinterpret_cast<const float4*>(g.prelu_vec + n);
+                o.x = prelu(o.x, sv.x); o.y = prelu(o.y, sv.y);
+                o.z = prelu(o.z, sv.z); o.w = prelu(o.w, sv.w);
             }
             if (g.R) {
                 const float4 rr = *reinterpret_cast<const float4*>(g.R + coff + n);
@@ -182,22 +196,21 @@ inline cudaError_t configure_rows_gemm() {
 }
 
 template <int BM, int BN, int TM, int TN>
-inline cudaError_t launch_rows_gemm_cfg(const GemmArgs& g, cudaStream_t st) {
+inline cudaError_t launch_rows_gemm_cfg(const GemmArgs& g, cudaStream_t st, bool pdl) {
     constexpr int NT = (BM / TM) * (BN / TN);
     const size_t smem = (size_t)(GK * (BM + 4) + GK * BN) * sizeof(float);
     dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-    rows_gemm_kernel<BM, BN, TM, TN><<<grid, NT, smem, st>>>(g);
-    return cudaGetLastError();
+    return launch_k(pdl, rows_gemm_kernel<BM, BN, TM, TN>, grid, dim3(NT), smem, st, g);
 }
 
 // Pick a tile by problem size: small M (one streaming frame = 97 rows) wants many small CTAs,
 // large M wants the 64x128 tile.  N must be a multiple of 64; K a multiple of 64.
-inline cudaError_t launch_rows_gemm(const GemmArgs& g, cudaStream_t st) {
+inline cudaError_t launch_rows_gemm(const GemmArgs& g, cudaStream_t st, bool pdl = false) {
     if (g.N % 64 != 0 || g.K % 64 != 0 || g.M <= 0) return cudaErrorInvalidValue;
     if (g.ln_g && g.K != 64) return cudaErrorInvalidValue;
-    if (g.M <= 2048) return launch_rows_gemm_cfg<16, 64, 2, 4>(g, st);     // 128 threads
-    if (g.N % 128 == 0) return launch_rows_gemm_cfg<64, 128, 4, 8>(g, st); // 256 threads
-    return launch_rows_gemm_cfg<64, 64, 4, 4>(g, st);                      // 256 threads
+    if (g.M <= 2048) return launch_rows_gemm_cfg<16, 64, 2, 4>(g, st, pdl);     // 128 threads
+    if (g.N % 128 == 0) return launch_rows_gemm_cfg<64, 128, 4, 8>(g, st, pdl); // 256 threads
+    return launch_rows_gemm_cfg<64, 64, 4, 4>(g, st, pdl);                      // 256 threads
 }
 
 }  // namespace l2h

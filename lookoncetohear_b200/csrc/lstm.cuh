@@ -32,20 +32,27 @@ struct LstmArgs {
     int nseq, L;
     int inner_count;
     int64_t outer_stride, inner_stride, step_stride;
+    // rows of `out` may follow a different (e.g. zero-padded) layout; all zero => same as gx rows
+    int64_t out_outer_stride, out_inner_stride, out_step_stride;
     int ndir;              // 1 or 2; direction 1 runs the steps in reverse
 };
+
+constexpr int LSTM_STAGES = 8;   // cp.async ring depth for the precomputed input projection
 
 template <int NSEQ>
 __global__ void __launch_bounds__(256, (NSEQ <= 4 ? 2 : 1))
 lstm_rec_kernel(const LstmArgs a) {
     __shared__ __align__(16) float hbuf[2][NSEQ][64];
+    __shared__ __align__(16) float gs[LSTM_STAGES][NSEQ][256];   // gx rows, LSTM_STAGES steps in flight
 
+    griddep_launch();
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
     const int seq0 = blockIdx.x * NSEQ;
     const int j = tid >> 2, q = tid & 3;
 
-    // W_hh row (j*4+q) of this direction -> registers, as 32 k-pairs
+    // W_hh row (j*4+q) of this direction -> registers, as 32 k-pairs.  Independent of the chain:
+    // under PDL this overlaps the tail of the previous kernel.
     float2 w[32];
     {
         const float4* wp = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + tid) * 64);
@@ -56,83 +63,90 @@ lstm_rec_kernel(const LstmArgs a) {
             w[2 * k + 1] = make_float2(t.z, t.w);
         }
     }
+    griddep_wait();      // everything below reads what earlier kernels of the chain wrote
 
-    int64_t base[NSEQ], hc[NSEQ];
-    bool valid[NSEQ];
+    const bool own_out = (a.out_outer_stride | a.out_inner_stride | a.out_step_stride) != 0;
+    const int64_t o_step = (own_out ? a.out_step_stride : a.step_stride) * a.out_ld;   // floats per step
+    const int sgn = (dir == 0) ? 1 : -1;
+    const int first = (dir == 0) ? 0 : a.L - 1;
+
     float c[NSEQ];
+    bool valid[NSEQ];
+    float* outp[NSEQ];          // &out[row(seq, first)][dir*64 + j]
+    int64_t hc[NSEQ];
 #pragma unroll
     for (int s = 0; s < NSEQ; ++s) {
         const int seq = seq0 + s;
         valid[s] = seq < a.nseq;
         const int sq = valid[s] ? seq : 0;
-        base[s] = (int64_t)(sq / a.inner_count) * a.outer_stride + (int64_t)(sq % a.inner_count) * a.inner_stride;
-        hc[s] = (int64_t)(sq / a.inner_count) * a.hc_outer_stride + (int64_t)(sq % a.inner_count) * 64 + j;
+        const int so = sq / a.inner_count, si = sq % a.inner_count;
+        const int64_t ob = own_out ? (int64_t)so * a.out_outer_stride + (int64_t)si * a.out_inner_stride
+                                   : (int64_t)so * a.outer_stride + (int64_t)si * a.inner_stride;
+        outp[s] = a.out + ob * a.out_ld + (int64_t)first * o_step + dir * 64 + j;
+        hc[s] = (int64_t)so * a.hc_outer_stride + (int64_t)si * 64 + j;
         c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
         if (q == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
     }
 
-    const int64_t gcol = (int64_t)dir * 256 + tid;
-    auto step_of = [&](int it) { return dir == 0 ? it : a.L - 1 - it; };
-
-    // prefetch gx two steps ahead
-    float g0[NSEQ], g1[NSEQ];
-#pragma unroll
-    for (int s = 0; s < NSEQ; ++s) {
-        g0[s] = valid[s] ? __ldg(a.gx + (base[s] + (int64_t)step_of(0) * a.step_stride) * a.gx_ld + gcol) : 0.f;
-        g1[s] = (valid[s] && a.L > 1)
-                    ? __ldg(a.gx + (base[s] + (int64_t)step_of(1) * a.step_stride) * a.gx_ld + gcol) : 0.f;
+    // ---- gx ring: thread (cs = tid/64, chunk = tid%64) copies 16 B of sequence cs's row ----------
+    const int cs = tid >> 6, chunk = tid & 63;
+    const bool copier = cs < NSEQ && (seq0 + cs) < a.nseq;
+    const float* gsrc = nullptr;          // &gx[row(seq, first)][dir*256 + chunk*4]
+    const int64_t g_step = a.step_stride * a.gx_ld * sgn;
+    if (copier) {
+        const int sq = seq0 + cs;
+        const int64_t gb = (int64_t)(sq / a.inner_count) * a.outer_stride + (int64_t)(sq % a.inner_count) * a.inner_stride;
+        gsrc = a.gx + (gb + (int64_t)first * a.step_stride) * a.gx_ld + dir * 256 + chunk * 4;
     }
+    auto issue = [&](int it) {           // copy the row of iteration `it` into its ring stage
+        if (copier && it < a.L) cp_async16(&gs[it % LSTM_STAGES][cs][chunk * 4], gsrc + (int64_t)it * g_step);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int it = 0; it < LSTM_STAGES - 1; ++it) issue(it);
+    cp_async_wait<LSTM_STAGES - 2>();
     __syncthreads();
 
-    // activation constants: sigmoid for i,f,o ; tanh for g (q == 2):  y = A / (1 + exp(-S x)) + Bc
-    const float S = (q == 2) ? 2.f : 1.f;
+    // activation: sigmoid for i,f,o ; tanh for g (q == 2):  y = A / (1 + 2^(S x)) + Bc, S folds -log2(e)
+    const float S = (q == 2) ? -2.f * 1.4426950408889634f : -1.4426950408889634f;
     const float Aa = (q == 2) ? 2.f : 1.f;
     const float Bc = (q == 2) ? -1.f : 0.f;
-    const int lane = tid & 31;
-    const int qbase = lane & ~3;
+    const int qbase = (tid & 31) & ~3;
 
     int cur = 0;
     for (int it = 0; it < a.L; ++it) {
-        const int st = step_of(it);
-        float g2[NSEQ];
-        if (it + 2 < a.L) {
-#pragma unroll
-            for (int s = 0; s < NSEQ; ++s)
-                g2[s] = valid[s]
-                            ? __ldg(a.gx + (base[s] + (int64_t)step_of(it + 2) * a.step_stride) * a.gx_ld + gcol)
-                            : 0.f;
-        } else {
-#pragma unroll
-            for (int s = 0; s < NSEQ; ++s) g2[s] = 0.f;
-        }
+        issue(it + LSTM_STAGES - 1);
+        const int stg = it % LSTM_STAGES;
 #pragma unroll
         for (int s = 0; s < NSEQ; ++s) {
             const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][s][0]);
-            float2 acc0 = make_float2(g0[s], 0.f), acc1 = make_float2(0.f, 0.f);
+            float2 acc0 = make_float2(gs[stg][s][tid], 0.f), acc1 = make_float2(0.f, 0.f);
+            float2 acc2 = make_float2(0.f, 0.f), acc3 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float4 h4 = hp[k];
+            for (int k = 0; k < 16; k += 2) {
+                const float4 h4 = hp[k], h5 = hp[k + 1];
                 acc0 = ffma2(w[2 * k], make_float2(h4.x, h4.y), acc0);
                 acc1 = ffma2(w[2 * k + 1], make_float2(h4.z, h4.w), acc1);
+                acc2 = ffma2(w[2 * k + 2], make_float2(h5.x, h5.y), acc2);
+                acc3 = ffma2(w[2 * k + 3], make_float2(h5.z, h5.w), acc3);
             }
-            const float pre = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-            const float act = __fdividef(Aa, 1.f + __expf(-S * pre)) + Bc;
+            const float pre = ((acc0.x + acc0.y) + (acc1.x + acc1.y)) + ((acc2.x + acc2.y) + (acc3.x + acc3.y));
+            const float act = __fdividef(Aa, 1.f + ex2_ftz(S * pre)) + Bc;
             const float gi = __shfl_sync(0xffffffffu, act, qbase + 0);
             const float gf = __shfl_sync(0xffffffffu, act, qbase + 1);
             const float gg = __shfl_sync(0xffffffffu, act, qbase + 2);
             const float go = __shfl_sync(0xffffffffu, act, qbase + 3);
             c[s] = gf * c[s] + gi * gg;
-            const float h = go * fast_tanh(c[s]);
+            const float h = go * (__fdividef(2.f, 1.f + ex2_ftz(-2.f * 1.4426950408889634f * c[s])) - 1.f);
             if (q == 0) {
                 hbuf[cur ^ 1][s][j] = h;
-                if (valid[s])
-                    a.out[(base[s] + (int64_t)st * a.step_stride) * a.out_ld + dir * 64 + j] = h;
+                if (valid[s]) *outp[s] = h;
             }
-            g0[s] = g1[s];
-            g1[s] = g2[s];
+            outp[s] += sgn * o_step;
         }
         cur ^= 1;
-        __syncthreads();
+        cp_async_wait<LSTM_STAGES - 2>();   // the row of iteration it+1 has landed (own copies) ...
+        __syncthreads();                    // ... and everybody's copies + the new h are visible
     }
 
     if (a.h_state != nullptr) {
@@ -146,7 +160,7 @@ lstm_rec_kernel(const LstmArgs a) {
     }
 }
 
-inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st) {
+inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st, bool pdl = false) {
     if (a.nseq <= 0 || a.L <= 0) return cudaErrorInvalidValue;
     // smallest NSEQ that still fits one wave of 148 SMs x 2 CTAs
     const int slots = 296;
@@ -154,11 +168,10 @@ inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st) {
     while (nseq_per < 4 && ((a.nseq + nseq_per - 1) / nseq_per) * a.ndir > slots) nseq_per *= 2;
     dim3 grid((a.nseq + nseq_per - 1) / nseq_per, a.ndir);
     switch (nseq_per) {
-        case 1: lstm_rec_kernel<1><<<grid, 256, 0, st>>>(a); break;
-        case 2: lstm_rec_kernel<2><<<grid, 256, 0, st>>>(a); break;
-        default: lstm_rec_kernel<4><<<grid, 256, 0, st>>>(a); break;
+        case 1: return launch_k(pdl, lstm_rec_kernel<1>, grid, dim3(256), 0, st, a);
+        case 2: return launch_k(pdl, lstm_rec_kernel<2>, grid, dim3(256), 0, st, a);
+        default: return launch_k(pdl, lstm_rec_kernel<4>, grid, dim3(256), 0, st, a);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace l2h

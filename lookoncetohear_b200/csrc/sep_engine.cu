@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -55,6 +56,7 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
+    bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
 };
 
 static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
@@ -196,8 +198,17 @@ static void resolve_pointers(SepEngine* e) {
 
 // ---- workspace carve-up (floats) ---------------------------------------------------------------
 struct Workspace {
-    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, TAPS, total;
+    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, PART, TAPS, total;
 };
+// few frames in flight -> split every head's 50-row window over several CTAs
+static int attn_splits(int B, int T) {
+    const int ctas = B * T * NHEAD;
+    if (ctas >= 148) return 1;
+    if (ctas * 2 >= 148) return 2;
+    if (ctas * 5 >= 148) return 5;
+    return 10;
+}
+
 static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     Workspace ws;
     const int64_t rows = (int64_t)B * T * NF;
@@ -211,6 +222,7 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.KALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * QK_LD : 0);
     ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
     ws.PRE = alloc((int64_t)B * FC);
+    ws.PART = alloc(attn_splits(B, T) > 1 ? (int64_t)B * T * NHEAD * attn_splits(B, T) * PART_LD : 0);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
     ws.total = cur;
     return ws;
@@ -262,7 +274,8 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     if (rows > 0x7fffffff / 2) return fail(1, "batch*frames too large for one call; split the batch");
     float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
     float* Q = wsp + ws.Q; float* KALL = wsp + ws.KALL; float* VALL = wsp + ws.VALL; float* PRE = wsp + ws.PRE;
-    float* TAPS = wsp + ws.TAPS;
+    float* TAPS = wsp + ws.TAPS; float* PART = wsp + ws.PART;
+    const int nsplit = attn_splits(B, T);
     int tap = 0;
     auto do_tap = [&]() -> int {
         if (flags & L2H_FLAG_TAPS) {
@@ -272,16 +285,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         return 0;
     };
     float* sbase = state + sizeof(StateHeader) / 4;
+    const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS);
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
-    front_kernel<<<dim3(T, B), 256, 0, st>>>(x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel);
-    CK(cudaGetLastError());
+    CK(launch_k(false, front_kernel, dim3(T, B), dim3(256), 0, st, x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel));
     MARK("front");
-    spk_gemv_kernel<<<dim3(FC / 32, B), 256, 0, st>>>(emb, PRE, state, ss, e->w);
-    CK(cudaGetLastError());
+    CK(launch_k(pdl, spk_gemv_kernel, dim3(FC / 32, B), dim3(256), 0, st, emb, PRE, (const float*)state, ss, e->w));
     MARK("spk_gemv");
-    spk_ln_kernel<<<B, 256, 0, st>>>(emb, PRE, state, ss, e->w);
-    CK(cudaGetLastError());
+    CK(launch_k(pdl, spk_ln_kernel, dim3(B), dim3(256), 0, st, emb, (const float*)PRE, state, ss, e->w));
     MARK("spk_ln");
     if (int rc = do_tap()) return rc;
 
@@ -291,25 +302,25 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         GemmArgs g{};
         g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
         g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
-        CK(launch_rows_gemm(g, st));
+        CK(launch_rows_gemm(g, st, pdl));
         MARK("gemm_ih_intra");
         LstmArgs l{};
         l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
         l.nseq = B * T; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1;
         l.ndir = 2;
-        CK(launch_lstm_rec(l, st));
+        CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_intra");
         g = GemmArgs{};
         g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
         g.M = (int)rows; g.N = 64; g.K = 128;
-        CK(launch_rows_gemm(g, st));
+        CK(launch_rows_gemm(g, st, pdl));
         MARK("gemm_lin_intra");
         if (int rc = do_tap()) return rc;
         // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
         g = GemmArgs{};
         g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
         g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
-        CK(launch_rows_gemm(g, st));
+        CK(launch_rows_gemm(g, st, pdl));
         MARK("gemm_ih_inter");
         l = LstmArgs{};
         l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
@@ -318,33 +329,33 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         l.hc_outer_stride = ss;
         l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
         l.step_stride = NF; l.ndir = 1;
-        CK(launch_lstm_rec(l, st));
+        CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_inter");
         g = GemmArgs{};
         g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
         g.M = (int)rows; g.N = 64; g.K = 64;
-        CK(launch_rows_gemm(g, st));
+        CK(launch_rows_gemm(g, st, pdl));
         MARK("gemm_lin_inter");
         if (int rc = do_tap()) return rc;
         // ---- attention --------------------------------------------------------------------------
         if (T > 1) {
-            kv_gather_kernel<<<dim3(ATT - 1, B * NHEAD), 128, 0, st>>>(state, ss, b, KALL, VALL, T);
-            CK(cudaGetLastError());
+            CK(launch_k(pdl, kv_gather_kernel, dim3(ATT - 1, B * NHEAD), dim3(128), 0, st, (const float*)state, ss, b, KALL,
+                        VALL, T));
             MARK("kv_gather");
         }
-        qkv_kernel<<<dim3(T, B), QKV_THREADS, QKV_SMEM, st>>>(X, Q, KALL, VALL, state, ss, b, W, T);
-        CK(cudaGetLastError());
+        CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X, Q, KALL, VALL, state, ss,
+                    b, W, T));
         MARK("qkv");
-        attn_kernel<<<dim3(T, NHEAD, B), 256, 0, st>>>(Q, KALL, VALL, state, ss, b, Z, T);
-        CK(cudaGetLastError());
+        CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD * nsplit, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
+                    (const float*)VALL, (const float*)state, ss, b, Z, PART, nsplit, T));
         MARK("attn");
-        attn_out_kernel<<<dim3(T, B), 256, AOUT_SMEM, st>>>(Z, X, state, ss, W, (b == 0 && e->n_blocks > 1) ? 1 : 0, T);
-        CK(cudaGetLastError());
+        CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
+                    (b == 0 && e->n_blocks > 1) ? 1 : 0, (const float*)PART, nsplit, T));
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
-    back_kernel<<<dim3(T, B), 256, BACK_SMEM, st>>>(X, y, ybs, ycs, y_len, state, ss, e->w, T, a.pos_rel);
-    CK(cudaGetLastError());
+    CK(launch_k(pdl, back_kernel, dim3(T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
+                a.pos_rel));
     MARK("back");
 #undef MARK
     return 0;
@@ -399,6 +410,7 @@ int l2h_sep_create(const l2h_sep_config* c, void** handle) {
     SepEngine* e = new SepEngine();
     e->cfg = *c;
     e->n_blocks = c->B;
+    if (const char* v = getenv("L2H_PDL")) e->use_pdl = atoi(v) != 0;
     build_layout(e);
     *handle = e;
     return 0;

@@ -74,6 +74,8 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
              int pos_rel) {
     __shared__ float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
+    griddep_launch();
+    griddep_wait();
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
@@ -99,12 +101,19 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
         float acc[3][NMIC];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-        for (int n = 0; n < NFFT; ++n) {
-            const float wv = __ldg(w.wat + n * 196 + tid);
+        // 16 independent filter loads in flight per thread (the loop is L2-latency bound otherwise)
+#pragma unroll 1
+        for (int n0 = 0; n0 < NFFT; n0 += 16) {
+            float wv[16];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                acc[i][0] = fmaf(wv, xs[0][HOP * i + n], acc[i][0]);
-                acc[i][1] = fmaf(wv, xs[1][HOP * i + n], acc[i][1]);
+            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w.wat + (n0 + u) * 196 + tid);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    acc[i][0] = fmaf(wv[u], xs[0][HOP * i + n0 + u], acc[i][0]);
+                    acc[i][1] = fmaf(wv[u], xs[1][HOP * i + n0 + u], acc[i][1]);
+                }
             }
         }
         const int ri = tid / NF, f = tid % NF;      // rows 0..96 real, 97..193 imaginary
@@ -155,6 +164,8 @@ __global__ void __launch_bounds__(256)
 spk_gemv_kernel(const float* __restrict__ emb, float* __restrict__ pre, const float* __restrict__ state,
                 int64_t sstride, SepWeights w) {
     __shared__ __align__(16) float es[SPK];
+    griddep_launch();
+    griddep_wait();
     const int b = blockIdx.y, tid = threadIdx.x;
     const float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float e = emb[(int64_t)b * SPK + tid];
@@ -180,6 +191,8 @@ __global__ void __launch_bounds__(256)
 spk_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pre, float* __restrict__ state,
               int64_t sstride, SepWeights w) {
     __shared__ float red[32];
+    griddep_launch();
+    griddep_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float e = emb[(int64_t)b * SPK + tid];
@@ -204,6 +217,8 @@ spk_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pre, floa
 // pos-49 .. pos-1 (never-written slots are zero = the reference's zero-initialised K_buf/V_buf).
 __global__ void kv_gather_kernel(const float* __restrict__ state, int64_t sstride, int blk,
                                  float* __restrict__ Kall, float* __restrict__ Vall, int T) {
+    griddep_launch();
+    griddep_wait();
     const int i = blockIdx.x, bh = blockIdx.y, b = bh / NHEAD, h = bh % NHEAD;
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const long long fr = hdr->pos - (ATT - 1) + i;
@@ -236,13 +251,17 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
     float* Ws = Xt + 64 * 100;           // [64][112]
     float* P = Ws + 64 * NQKV;           // [97][113]
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const float* xr = X + ((int64_t)b * T + t) * NF * CH;
-    for (int i = tid; i < 100 * 64; i += QKV_THREADS) {
-        const int f = i / 64, k = i % 64;
-        Xt[k * 100 + f] = (f < NF) ? xr[f * CH + k] : 0.f;
-    }
-    for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)
+    griddep_launch();
+    for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)      // weights: independent of the chain
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wqkv_t) + i);
+    griddep_wait();
+    const float* xr = X + ((int64_t)b * T + t) * NF * CH;
+    for (int i = tid; i < 100 * 16; i += QKV_THREADS) {       // float4 loads; lanes along f -> conflict-free stores
+        const int c4 = i / 100, f = i % 100;
+        const float4 v = (f < NF) ? *reinterpret_cast<const float4*>(xr + f * CH + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        Xt[(c4 * 4 + 0) * 100 + f] = v.x; Xt[(c4 * 4 + 1) * 100 + f] = v.y;
+        Xt[(c4 * 4 + 2) * 100 + f] = v.z; Xt[(c4 * 4 + 3) * 100 + f] = v.w;
+    }
     __syncthreads();
     // 4 rows x 4 cols register tiles: 25 row groups x 28 col groups
     for (int it = tid; it < 25 * 28; it += QKV_THREADS) {
@@ -320,15 +339,24 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
 
 // ------------------------------------------------------------------------------------------
 // K4b local attention: each query attends to its own frame + the 49 previous ones, unmasked
-// (tfgridnet_causal.py:564-581).  grid (T, 4, B), 256 threads.
+// (tfgridnet_causal.py:564-581).  grid (T, 4*nsplit, B), 256 threads.
 // T == 1: K/V rows are the 50 ring slots (order is irrelevant to softmax-weighted sums);
 // T  > 1: rows t .. t+49 of the linear scratch.
+// nsplit > 1 (few frames in flight): the 50 rows of a head are split over nsplit CTAs, each writing
+// an un-normalised partial (max, sum, o[1552]) that attn_out_kernel merges (flash-decoding style).
+constexpr int PART_LD = V_DIM + 4;      // [o (1552) | m | l | pad pad]
+
 __global__ void __launch_bounds__(256)
 attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
-            const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T) {
+            const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z,
+            float* __restrict__ part, int nsplit, int T) {
     __shared__ __align__(16) float qs[QK_LD];
     __shared__ float sc[64];
-    const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    griddep_launch();
+    griddep_wait();
+    const int t = blockIdx.x, h = blockIdx.y / nsplit, sp = blockIdx.y % nsplit, b = blockIdx.z, tid = threadIdx.x;
+    const int rows_per = (ATT + nsplit - 1) / nsplit;
+    const int j0 = sp * rows_per, j1 = min(ATT, j0 + rows_per), nr = j1 - j0;
     const int64_t bh = (int64_t)b * NHEAD + h;
     const float* kb;
     const float* vb;
@@ -340,48 +368,80 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
         kb = Kall + (bh * (ATT - 1 + T) + t) * QK_LD;
         vb = Vall + (bh * (ATT - 1 + T) + t) * V_DIM;
     }
+    kb += (int64_t)j0 * QK_LD;
+    vb += (int64_t)j0 * V_DIM;
     const float* q = Qbuf + (bh * T + t) * QK_LD;
     for (int i = tid; i < QK_LD / 4; i += 256)
         reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(q)[i];
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     const float scale = rsqrtf((float)QK_DIM);
-    for (int j = warp; j < ATT; j += 8) {
+    for (int j = warp; j < nr; j += 8) {
         const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)j * QK_LD);
+        float4 kv[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = lane + 32 * u;
+            kv[u] = (i < QK_LD / 4) ? kr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float s = 0.f;
-        for (int i = lane; i < QK_LD / 4; i += 32) {
-            const float4 kv = kr[i];
-            const float4 qv = reinterpret_cast<const float4*>(qs)[i];
-            s += kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = lane + 32 * u;
+            if (i < QK_LD / 4) {
+                const float4 qv = reinterpret_cast<const float4*>(qs)[i];
+                s += kv[u].x * qv.x + kv[u].y * qv.y + kv[u].z * qv.z + kv[u].w * qv.w;
+            }
         }
         s = warp_sum(s);
         if (lane == 0) sc[j] = s * scale;
     }
     __syncthreads();
+    float mx = -INFINITY, lsum = 0.f;
     if (warp == 0) {
-        const float a0 = (lane < ATT) ? sc[lane] : -INFINITY;
-        const float a1 = (lane + 32 < ATT) ? sc[lane + 32] : -INFINITY;
-        const float mx = warp_max(fmaxf(a0, a1));
-        const float e0 = (lane < ATT) ? __expf(a0 - mx) : 0.f;
-        const float e1 = (lane + 32 < ATT) ? __expf(a1 - mx) : 0.f;
-        const float inv = 1.f / warp_sum(e0 + e1);
-        if (lane < ATT) sc[lane] = e0 * inv;
-        if (lane + 32 < ATT) sc[lane + 32] = e1 * inv;
+        const float a0 = (lane < nr) ? sc[lane] : -INFINITY;
+        const float a1 = (lane + 32 < nr) ? sc[lane + 32] : -INFINITY;
+        mx = warp_max(fmaxf(a0, a1));
+        const float e0 = (lane < nr) ? __expf(a0 - mx) : 0.f;
+        const float e1 = (lane + 32 < nr) ? __expf(a1 - mx) : 0.f;
+        lsum = warp_sum(e0 + e1);
+        const float inv = (nsplit == 1) ? 1.f / lsum : 1.f;
+        if (lane < nr) sc[lane] = e0 * inv;
+        if (lane + 32 < nr) sc[lane + 32] = e1 * inv;
     }
     __syncthreads();
     float* zr = Z + ((int64_t)b * T + t) * NF * CH;
+    float* pr = part + ((((int64_t)b * T + t) * NHEAD + h) * nsplit + sp) * PART_LD;
     for (int c4 = tid; c4 < V_DIM / 4; c4 += 256) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nr <= 5) {                      // split mode: all rows in flight at once
+            float4 v[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float p = (j < nr) ? sc[j] : 0.f;
+                acc.x = fmaf(p, v[j].x, acc.x); acc.y = fmaf(p, v[j].y, acc.y);
+                acc.z = fmaf(p, v[j].z, acc.z); acc.w = fmaf(p, v[j].w, acc.w);
+            }
+        } else {
 #pragma unroll 10
-        for (int j = 0; j < ATT; ++j) {
-            const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4];
-            const float p = sc[j];
-            acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
-            acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+            for (int j = 0; j < nr; ++j) {
+                const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4];
+                const float p = sc[j];
+                acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
+                acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+            }
         }
-        const int f = c4 >> 2, c0 = (c4 & 3) * 4;            // feature f*16 + c -> channel h*16 + c
-        *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
+        if (nsplit == 1) {
+            const int f = c4 >> 2, c0 = (c4 & 3) * 4;        // feature f*16 + c -> channel h*16 + c
+            *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
+        } else {
+            *reinterpret_cast<float4*>(pr + c4 * 4) = acc;
+        }
     }
+    if (nsplit > 1 && tid == 0) { pr[V_DIM] = mx; pr[V_DIM + 1] = lsum; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -392,20 +452,61 @@ constexpr size_t AOUT_SMEM = (size_t)(64 * 100 + 64 * 64 + NF * 64) * sizeof(flo
 
 __global__ void __launch_bounds__(256)
 attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float* __restrict__ state,
-                int64_t sstride, BlockWeights w, int apply_gate, int T) {
+                int64_t sstride, BlockWeights w, int apply_gate, const float* __restrict__ part, int nsplit, int T) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
+    __shared__ float coef[NHEAD][16];
     float* Zt = sm;                 // [64][100]
     float* Ws = Zt + 64 * 100;      // [64][64]
     float* P = Ws + 64 * 64;        // [97][64]
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
-    for (int i = tid; i < 100 * 64; i += 256) {
-        const int f = i / 64, k = i % 64;
-        Zt[k * 100 + f] = (f < NF) ? zr[f * CH + k] : 0.f;
-    }
+    griddep_launch();
     for (int i = tid; i < 64 * 64 / 4; i += 256)
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wp_t) + i);
+    griddep_wait();
+    if (nsplit == 1) {
+        const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
+        for (int i = tid; i < 100 * 16; i += 256) {
+            const int c4 = i / 100, f = i % 100;
+            const float4 v = (f < NF) ? *reinterpret_cast<const float4*>(zr + f * CH + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            Zt[(c4 * 4 + 0) * 100 + f] = v.x; Zt[(c4 * 4 + 1) * 100 + f] = v.y;
+            Zt[(c4 * 4 + 2) * 100 + f] = v.z; Zt[(c4 * 4 + 3) * 100 + f] = v.w;
+        }
+    } else {                                   // merge the split-attention partials
+        const float* pb = part + ((int64_t)b * T + t) * NHEAD * nsplit * PART_LD;
+        if (tid < NHEAD) {
+            float mstar = -INFINITY;
+            for (int s2 = 0; s2 < nsplit; ++s2) mstar = fmaxf(mstar, pb[(tid * nsplit + s2) * PART_LD + V_DIM]);
+            float den = 0.f;
+            for (int s2 = 0; s2 < nsplit; ++s2) {
+                const float wgt = __expf(pb[(tid * nsplit + s2) * PART_LD + V_DIM] - mstar);
+                coef[tid][s2] = wgt;
+                den += wgt * pb[(tid * nsplit + s2) * PART_LD + V_DIM + 1];
+            }
+            const float inv = 1.f / den;
+            for (int s2 = 0; s2 < nsplit; ++s2) coef[tid][s2] *= inv;
+        }
+        __syncthreads();
+        for (int i = tid; i < 3 * 64; i += 256) Zt[(i % 64) * 100 + NF + i / 64] = 0.f;     // pad rows 97..99
+        for (int i = tid; i < NF * NHEAD * 4; i += 256) {       // item = (f, head, 4 channels)
+            const int c4 = i & 3, hh = (i >> 2) & 3, f = i >> 4;
+            float4 v[10];
+#pragma unroll
+            for (int s2 = 0; s2 < 10; ++s2)
+                v[s2] = (s2 < nsplit) ? *reinterpret_cast<const float4*>(pb + (hh * nsplit + s2) * PART_LD + f * VD + c4 * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int s2 = 0; s2 < 10; ++s2) {
+                const float cf = (s2 < nsplit) ? coef[hh][s2] : 0.f;
+                o.x = fmaf(cf, v[s2].x, o.x); o.y = fmaf(cf, v[s2].y, o.y);
+                o.z = fmaf(cf, v[s2].z, o.z); o.w = fmaf(cf, v[s2].w, o.w);
+            }
+            const int k = hh * VD + c4 * 4;
+            Zt[(k + 0) * 100 + f] = o.x; Zt[(k + 1) * 100 + f] = o.y;
+            Zt[(k + 2) * 100 + f] = o.z; Zt[(k + 3) * 100 + f] = o.w;
+        }
+    }
     __syncthreads();
     const float slope = __ldg(w.slopes + 3);
     for (int it = tid; it < 25 * 16; it += 256) {
@@ -450,10 +551,18 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     const float rs = rsqrtf(block_sum(q, red) * (1.f / FC) + 1e-5f);
     float* xr = X + ((int64_t)b * T + t) * NF * CH;
     const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
-    for (int i = tid; i < FC; i += 256) {
-        float v = xr[i] + (P[i] - mu) * rs * __ldg(w.lnp_g + i) + __ldg(w.lnp_b + i);
-        if (apply_gate) v *= gate[i];
-        xr[i] = v;
+    for (int i = tid; i < FC / 4; i += 256) {
+        float4 x4 = reinterpret_cast<float4*>(xr)[i];
+        const float4 p4 = reinterpret_cast<const float4*>(P)[i];
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.lnp_g) + i);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.lnp_b) + i);
+        x4.x += (p4.x - mu) * rs * g4.x + b4.x; x4.y += (p4.y - mu) * rs * g4.y + b4.y;
+        x4.z += (p4.z - mu) * rs * g4.z + b4.z; x4.w += (p4.w - mu) * rs * g4.w + b4.w;
+        if (apply_gate) {
+            const float4 t4 = reinterpret_cast<const float4*>(gate)[i];
+            x4.x *= t4.x; x4.y *= t4.y; x4.z *= t4.z; x4.w *= t4.w;
+        }
+        reinterpret_cast<float4*>(xr)[i] = x4;
     }
 }
 
@@ -473,6 +582,8 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     float* outs = R + 2 * NSRC * NROW;    // [2 ears][128]
     float* tails = outs + NSRC * HOP;     // [2 ears][64]  w_{t-1}[128..191]
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    griddep_launch();
+    griddep_wait();
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
     const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
@@ -482,15 +593,15 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
     float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
 
-    for (int i = tid; i < 4 * 99 * 64; i += 256) {
-        const int slot = i / (99 * 64), r = (i / 64) % 99, c = i % 64;
+    for (int i = tid; i < 4 * 99 * 16; i += 256) {          // float4 granularity
+        const int slot = i / (99 * 16), r = (i / 16) % 99, c4 = i % 16;
         const int tt = t - 3 + slot, f = r - 1;
-        float v = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f >= 0 && f < NF) {
-            if (tt >= 0) v = X[(((int64_t)b * T + tt) * NF + f) * CH + c];
-            else if (tt >= -2) v = db[(2 + tt) * FC + f * CH + c];
+            if (tt >= 0) v = *reinterpret_cast<const float4*>(X + (((int64_t)b * T + tt) * NF + f) * CH + c4 * 4);
+            else if (tt >= -2) v = *reinterpret_cast<const float4*>(db + (2 + tt) * FC + f * CH + c4 * 4);
         }
-        Xs[i] = v;
+        reinterpret_cast<float4*>(Xs)[i] = v;
     }
     __syncthreads();
     // deconv for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
@@ -535,7 +646,16 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
         const int fi = (n < HOP) ? 1 : 0;
         const float* rr = R + (fi * NSRC + ear) * NROW;
         float acc = 0.f;
-        for (int r = 0; r < NROW; ++r) acc = fmaf(rr[r], __ldg(w.ws + r * NFFT + n), acc);
+#pragma unroll 1
+        for (int r0 = 0; r0 < 192; r0 += 16) {               // 16 filter loads in flight
+            float wv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w.ws + (r0 + u) * NFFT + n);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fmaf(rr[r0 + u], wv[u], acc);
+        }
+        acc = fmaf(rr[192], __ldg(w.ws + 192 * NFFT + n), acc);
+        acc = fmaf(rr[193], __ldg(w.ws + 193 * NFFT + n), acc);
         if (n < HOP) outs[ear * HOP + n] = acc;
         else tails[ear * LOOKAHEAD + (n - HOP)] = acc;
     }

@@ -99,3 +99,22 @@ def test_mirror_module_matches_reference_layout(tsh_params):
     assert tuple(sd["tfgridnet.enc.filterbank._filters"].shape) == (194, 1, 192)
     assert tuple(sd["tfgridnet.blocks.2.attn_conv_V.3.norm.weight"].shape) == (1552,)
     assert tuple(sd["tfgridnet.embed_to_feats_proj.0.weight"].shape) == (6208, 256)
+
+
+def test_embed_weight_table_matches_reference_state_dict(lib, embed_params):
+    from lookoncetohear_b200 import EmbedTFGridNet
+    net = EmbedTFGridNet(**embed_params)
+    assert sum(p.numel() for p in net.parameters()) == 2_368_681
+    h = net._engine()
+    for k, v in net.state_dict().items():
+        host = v.detach().float().contiguous()
+        assert lib.l2h_embed_load_weight(h, k.encode(), host.data_ptr(), host.numel()) == 0, k
+    ne, nl = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.l2h_embed_weights_expected(h, ctypes.byref(ne), ctypes.byref(nl)) == 0
+    assert ne.value == nl.value == len(net.state_dict())
+    n = ctypes.c_size_t()
+    assert lib.l2h_embed_workspace_bytes(h, 1, 80000, ctypes.byref(n)) == 0 and n.value > 0
+    mb = ctypes.c_int32()
+    assert lib.l2h_embed_max_batch(h, 80000, ctypes.byref(mb)) == 0 and mb.value >= 1
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 8000))
