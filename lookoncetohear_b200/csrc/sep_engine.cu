@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "lstm.cuh"
 #include "sep_kernels.cuh"
+#include "mid_kernel.cuh"
 
 namespace l2h {
 
@@ -56,6 +57,7 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
+    bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
 };
 
@@ -139,9 +141,16 @@ static void build_layout(SepEngine* e) {
         bind(&W.wih1_t, wih1); bind(&W.b1, b1); bind(&W.whh1, whh1);
         bind(&W.wl1_t, transposed(B + "intra_linear.weight", 64, 128, 64));
         bind(&W.bl1, plain(B + "intra_linear.bias", 64));
-        const int64_t wih2 = alloc(64 * 256), b2 = alloc(256), whh2 = alloc(256 * 64);
+        const int64_t wih2 = alloc(64 * 256), b2 = alloc(256), whh2 = alloc(256 * 64), whh2t = alloc(64 * 256);
         ih(B + "inter_rnn.weight_ih_l0", wih2, 256, 0);
-        hh(B + "inter_rnn.weight_hh_l0", whh2);
+        S[B + "inter_rnn.weight_hh_l0"] = Slot{whh2, 256 * 64, [whh2, whh2t](const float* s, float* d) {
+            for (int p = 0; p < 256; ++p) {
+                const int r = perm_row(p);
+                memcpy(d + whh2 + (int64_t)p * 64, s + r * 64, 64 * sizeof(float));
+                for (int k = 0; k < 64; ++k) d[whh2t + (int64_t)k * 256 + p] = s[r * 64 + k];
+            }
+        }};
+        bind(&W.whh2_t, whh2t);
         bias(B + "inter_rnn.bias_ih_l0", b2, true);
         bias(B + "inter_rnn.bias_hh_l0", b2, true);
         bind(&W.wih2_t, wih2); bind(&W.b2, b2); bind(&W.whh2, whh2);
@@ -190,7 +199,7 @@ static void resolve_pointers(SepEngine* e) {
     fixp(w.wd); fixp(w.bd);
     for (auto& W : e->bw) {
         fixp(W.ln1_g); fixp(W.ln1_b); fixp(W.wih1_t); fixp(W.b1); fixp(W.whh1); fixp(W.wl1_t); fixp(W.bl1);
-        fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.wl2_t); fixp(W.bl2);
+        fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.whh2_t); fixp(W.wl2_t); fixp(W.bl2);
         fixp(W.wqkv_t); fixp(W.bqkv); fixp(W.slopes); fixp(W.lnq_g); fixp(W.lnq_b); fixp(W.lnk_g);
         fixp(W.lnk_b); fixp(W.lnv_g); fixp(W.lnv_b); fixp(W.wp_t); fixp(W.bp); fixp(W.lnp_g); fixp(W.lnp_b);
     }
@@ -198,7 +207,7 @@ static void resolve_pointers(SepEngine* e) {
 
 // ---- workspace carve-up (floats) ---------------------------------------------------------------
 struct Workspace {
-    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, PART, TAPS, total;
+    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, PART, QKVRAW, TAPS, total;
 };
 // few frames in flight -> split every head's 50-row window over several CTAs
 static int attn_splits(int B, int T) {
@@ -223,6 +232,7 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
     ws.PRE = alloc((int64_t)B * FC);
     ws.PART = alloc(attn_splits(B, T) > 1 ? (int64_t)B * T * NHEAD * attn_splits(B, T) * PART_LD : 0);
+    ws.QKVRAW = alloc(T == 1 ? (int64_t)B * NF * NQKV : 0);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
     ws.total = cur;
     return ws;
@@ -234,6 +244,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
+    CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(configure_rows_gemm());
     g_attr_done = true;
     return 0;
@@ -275,7 +286,11 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
     float* Q = wsp + ws.Q; float* KALL = wsp + ws.KALL; float* VALL = wsp + ws.VALL; float* PRE = wsp + ws.PRE;
     float* TAPS = wsp + ws.TAPS; float* PART = wsp + ws.PART;
+    float* QKVRAW = wsp + ws.QKVRAW;
     const int nsplit = attn_splits(B, T);
+    // one-frame calls: the row-local middle of every block runs as ONE fused kernel (mid_kernel.cuh).
+    // (Taps want the intermediate activations of the generic chain, so they keep it.)
+    const bool fused_mid = (T == 1) && e->use_mid && !(flags & L2H_FLAG_TAPS);
     int tap = 0;
     auto do_tap = [&]() -> int {
         if (flags & L2H_FLAG_TAPS) {
@@ -310,41 +325,47 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         l.ndir = 2;
         CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_intra");
+        if (fused_mid) {
+            CK(launch_k(pdl, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW,
+                        state, ss, b, W));
+            MARK("mid");
+        } else {
         g = GemmArgs{};
-        g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
-        g.M = (int)rows; g.N = 64; g.K = 128;
-        CK(launch_rows_gemm(g, st, pdl));
-        MARK("gemm_lin_intra");
-        if (int rc = do_tap()) return rc;
-        // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
-        g = GemmArgs{};
-        g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
-        g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
-        CK(launch_rows_gemm(g, st, pdl));
-        MARK("gemm_ih_inter");
-        l = LstmArgs{};
-        l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
-        l.h_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
-        l.c_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_C;
-        l.hc_outer_stride = ss;
-        l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
-        l.step_stride = NF; l.ndir = 1;
-        CK(launch_lstm_rec(l, st, pdl));
-        MARK("lstm_inter");
-        g = GemmArgs{};
-        g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
-        g.M = (int)rows; g.N = 64; g.K = 64;
-        CK(launch_rows_gemm(g, st, pdl));
-        MARK("gemm_lin_inter");
-        if (int rc = do_tap()) return rc;
+            g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
+            g.M = (int)rows; g.N = 64; g.K = 128;
+            CK(launch_rows_gemm(g, st, pdl));
+            MARK("gemm_lin_intra");
+            if (int rc = do_tap()) return rc;
+            // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
+            g = GemmArgs{};
+            g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
+            g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
+            CK(launch_rows_gemm(g, st, pdl));
+            MARK("gemm_ih_inter");
+            l = LstmArgs{};
+            l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
+            l.h_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
+            l.c_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_C;
+            l.hc_outer_stride = ss;
+            l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
+            l.step_stride = NF; l.ndir = 1;
+            CK(launch_lstm_rec(l, st, pdl));
+            MARK("lstm_inter");
+            g = GemmArgs{};
+            g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
+            g.M = (int)rows; g.N = 64; g.K = 64;
+            CK(launch_rows_gemm(g, st, pdl));
+            MARK("gemm_lin_inter");
+            if (int rc = do_tap()) return rc;
+        }
         // ---- attention --------------------------------------------------------------------------
         if (T > 1) {
             CK(launch_k(pdl, kv_gather_kernel, dim3(ATT - 1, B * NHEAD), dim3(128), 0, st, (const float*)state, ss, b, KALL,
                         VALL, T));
             MARK("kv_gather");
         }
-        CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X, Q, KALL, VALL, state, ss,
-                    b, W, T));
+        CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
+                    (const float*)(fused_mid ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T));
         MARK("qkv");
         CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD * nsplit, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
                     (const float*)VALL, (const float*)state, ss, b, Z, PART, nsplit, T));
@@ -411,6 +432,7 @@ int l2h_sep_create(const l2h_sep_config* c, void** handle) {
     e->cfg = *c;
     e->n_blocks = c->B;
     if (const char* v = getenv("L2H_PDL")) e->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("L2H_MID")) e->use_mid = atoi(v) != 0;
     build_layout(e);
     *handle = e;
     return 0;
@@ -512,7 +534,7 @@ int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* off, 
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !n) return fail(1, "bad argument");
-    *n = 3 + e->n_blocks * (9 + (frames > 1 ? 1 : 0)) + 1;
+    *n = 3 + e->n_blocks * (frames == 1 && e->use_mid ? 6 : 9 + (frames > 1 ? 1 : 0)) + 1;
     return 0;
 }
 

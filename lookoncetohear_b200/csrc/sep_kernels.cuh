@@ -30,7 +30,8 @@ struct BlockWeights {
     const float *ln2_g, *ln2_b;
     const float* wih2_t;              // [64][256]
     const float* b2;                  // [256]
-    const float* whh2;                // [256][64]
+    const float* whh2;                // [256][64]   (row = gate column j*4+q)
+    const float* whh2_t;              // [64][256]   the same matrix k-major (mid_kernel)
     const float* wl2_t;               // [64][64]
     const float* bl2;
     const float* wqkv_t;              // [64][112]   cols: Q(h*6+e) | K(h*6+e) | V(h*16+c)
@@ -243,8 +244,8 @@ constexpr int QKV_PLD = 113;
 constexpr size_t QKV_SMEM = (size_t)(64 * 100 + 64 * NQKV + NF * QKV_PLD) * sizeof(float);
 
 __global__ void __launch_bounds__(QKV_THREADS)
-qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restrict__ Kall,
-           float* __restrict__ Vall, float* __restrict__ state, int64_t sstride, int blk,
+qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __restrict__ Qbuf,
+           float* __restrict__ Kall, float* __restrict__ Vall, float* __restrict__ state, int64_t sstride, int blk,
            BlockWeights w, int T) {
     extern __shared__ __align__(16) float sm[];
     float* Xt = sm;                      // [64][100]  k-major, rows padded to 100 (zeros)
@@ -252,9 +253,19 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
     float* P = Ws + 64 * NQKV;           // [97][113]
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     griddep_launch();
-    for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)      // weights: independent of the chain
-        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wqkv_t) + i);
+    if (pre == nullptr)
+        for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)  // weights: independent of the chain
+            reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wqkv_t) + i);
     griddep_wait();
+    if (pre != nullptr) {            // projections already done by mid_kernel: just stage them
+        const float4* src = reinterpret_cast<const float4*>(pre + ((int64_t)b * T + t) * NF * NQKV);
+        for (int i = tid; i < NF * NQKV / 4; i += QKV_THREADS) {
+            const float4 v = src[i];
+            const int f = (i * 4) / NQKV, n = (i * 4) % NQKV;     // NQKV % 4 == 0: a float4 never straddles rows
+            P[f * QKV_PLD + n + 0] = v.x; P[f * QKV_PLD + n + 1] = v.y;
+            P[f * QKV_PLD + n + 2] = v.z; P[f * QKV_PLD + n + 3] = v.w;
+        }
+    } else {
     const float* xr = X + ((int64_t)b * T + t) * NF * CH;
     for (int i = tid; i < 100 * 16; i += QKV_THREADS) {       // float4 loads; lanes along f -> conflict-free stores
         const int c4 = i / 100, f = i % 100;
@@ -296,6 +307,7 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
             }
         }
     }
+    }
     __syncthreads();
     // LayerNorm per (which, head): one warp each
     const int warp = tid >> 5, lane = tid & 31;
@@ -303,11 +315,28 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
     const int d = (which == 2) ? VD : QE;
     const int n = NF * d;
     const int col0 = (which == 2) ? (48 + h * VD) : (which * 24 + h * QE);
+    // element i = f*d + e lives at P[f][col0 + e]; walk (f, e) incrementally (no division in the loops)
+    const int f0 = lane / d, e0 = lane % d, df = 32 / d, de = 32 % d;
     float s = 0.f;
-    for (int i = lane; i < n; i += 32) s += P[(i / d) * QKV_PLD + col0 + (i % d)];
+    {
+        int f = f0, e2 = e0;
+        for (int i = lane; i < n; i += 32) {
+            s += P[f * QKV_PLD + col0 + e2];
+            e2 += de; f += df;
+            if (e2 >= d) { e2 -= d; ++f; }
+        }
+    }
     const float mu = warp_sum(s) / (float)n;
     float q = 0.f;
-    for (int i = lane; i < n; i += 32) { const float dv = P[(i / d) * QKV_PLD + col0 + (i % d)] - mu; q += dv * dv; }
+    {
+        int f = f0, e2 = e0;
+        for (int i = lane; i < n; i += 32) {
+            const float dv = P[f * QKV_PLD + col0 + e2] - mu;
+            q += dv * dv;
+            e2 += de; f += df;
+            if (e2 >= d) { e2 -= d; ++f; }
+        }
+    }
     const float rs = rsqrtf(warp_sum(q) / (float)n + 1e-5f);
     const float* gam = (which == 0) ? w.lnq_g : (which == 1 ? w.lnk_g : w.lnv_g);
     const float* bet = (which == 0) ? w.lnq_b : (which == 1 ? w.lnk_b : w.lnv_b);
@@ -326,10 +355,15 @@ qkv_kernel(const float* __restrict__ X, float* __restrict__ Qbuf, float* __restr
             dst1 = sb + (which == 1 ? BK_K : BK_V) + ((int64_t)h * ATT + slot) * ld;
         if (T > 1) dst0 = (which == 1 ? Kall : Vall) + (bh * (ATT - 1 + T) + (ATT - 1) + t) * ld;
     }
-    for (int i = lane; i < n; i += 32) {
-        const float v = (P[(i / d) * QKV_PLD + col0 + (i % d)] - mu) * rs * __ldg(gam + i) + __ldg(bet + i);
-        if (dst0) dst0[i] = v;
-        if (dst1) dst1[i] = v;
+    {
+        int f = f0, e2 = e0;
+        for (int i = lane; i < n; i += 32) {
+            const float v = (P[f * QKV_PLD + col0 + e2] - mu) * rs * __ldg(gam + i) + __ldg(bet + i);
+            if (dst0) dst0[i] = v;
+            if (dst1) dst1[i] = v;
+            e2 += de; f += df;
+            if (e2 >= d) { e2 -= d; ++f; }
+        }
     }
     if (which != 2 && lane < 2) {        // zero the two pad columns of 582 -> 584
         if (dst0) dst0[QK_DIM + lane] = 0.f;
