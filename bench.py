@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
     # section 6), so probe 1 thread vs all cores first and run the timed steps on the faster setting.
     sample_frames = 125
     allc = os.cpu_count() or 1
-    probe = {t: time_cpu_streaming(8, args.chunks_per_call, 1, t)[0] for t in sorted({1, allc})}
+    probe = {t: time_cpu_streaming(4, args.chunks_per_call, 1, t)[0] for t in sorted({1, min(allc, 8)})}
     threads = max(probe, key=probe.get)
     times = []
     kind = None
@@ -324,9 +324,11 @@ def main():
                         "whole-chain algorithmic rate: %.1f GB/s, %.2f TFLOP/s fp32" % (
                             value / world * BYTES_PER_FRAME / 1e9, value / world * FLOP_PER_FRAME / 1e12)}
         extras["kernel_us"] = {k: round(1e3 * v["ms_mean"], 2) for k, v in prof.items()}
-        if world == 1:
+        if world == 1 and not args.no_extras:
             allc = os.cpu_count() or 1
-            probe = {t: time_cpu_streaming(8, cpc, 1, t)[0] for t in sorted({1, allc})}   # short probe
+            # chunk-by-chunk streaming on CPU is dispatch-bound: more threads are slower (0.14 frames/s on 128
+            # threads vs 190 on one, measured); probe 1 thread vs min(all, 8) briefly and keep the faster
+            probe = {t: time_cpu_streaming(4, cpc, 1, t)[0] for t in sorted({1, min(allc, 8)})}
             threads = max(probe, key=probe.get)
             fps, kind, _ = time_cpu_streaming(125, cpc, 2, threads)
             cpu_base = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,

@@ -65,6 +65,35 @@ L2H_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 L2H_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: one instruction stages a whole
+// contiguous tile (weights, a frame's rows) in shared memory at full L2 bandwidth, instead of a
+// latency-bound LDG->STS loop.  Addresses and sizes must be multiples of 16 bytes.
+L2H_DEVINL unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+L2H_DEVINL void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+L2H_DEVINL void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+L2H_DEVINL void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+L2H_DEVINL void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// order earlier generic-proxy accesses of shared memory before later async-proxy (TMA) writes to it
+L2H_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+L2H_DEVINL void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
 // attribute may start while its predecessor drains; griddep_wait() blocks until the predecessor
 // grid has completed and flushed.  Every kernel of a chain calls griddep_launch() first (lets the

@@ -34,21 +34,21 @@ mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict
     float* x2T = hT + 64 * MID_RT;        // [64][RT]    X2, k-major
     float* gt = x2T + 64 * MID_RT;        // [RT][256]   gate pre-activations
 
+    __shared__ __align__(8) unsigned long long wbar;
     griddep_launch();
     const int tid = threadIdx.x, b = blockIdx.y;
     const int r0 = blockIdx.x * MID_RT;
     const int nr = min(MID_RT, NF - r0);
-    {   // ---- weights -> smem (independent of the chain) -----------------------------------------
-        const float4* s1 = reinterpret_cast<const float4*>(w.wl1_t);
-        const float4* s2 = reinterpret_cast<const float4*>(w.wih2_t);
-        const float4* s3 = reinterpret_cast<const float4*>(w.whh2_t);
-        const float4* s4 = reinterpret_cast<const float4*>(w.wl2_t);
-        const float4* s5 = reinterpret_cast<const float4*>(w.wqkv_t);
-        for (int i = tid; i < 128 * 64 / 4; i += 256) reinterpret_cast<float4*>(W1)[i] = __ldg(s1 + i);
-        for (int i = tid; i < 64 * 256 / 4; i += 256) reinterpret_cast<float4*>(W2)[i] = __ldg(s2 + i);
-        for (int i = tid; i < 64 * 256 / 4; i += 256) reinterpret_cast<float4*>(W3)[i] = __ldg(s3 + i);
-        for (int i = tid; i < 64 * 64 / 4; i += 256) reinterpret_cast<float4*>(W4)[i] = __ldg(s4 + i);
-        for (int i = tid; i < 64 * NQKV / 4; i += 256) reinterpret_cast<float4*>(W5)[i] = __ldg(s5 + i);
+    // ---- weights -> smem: five TMA bulk copies (independent of the chain, so issued before the wait)
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&wbar, (128 * 64 + 64 * 256 + 64 * 256 + 64 * 64 + 64 * NQKV) * 4);
+        tma_load_1d(W1, w.wl1_t, 128 * 64 * 4, &wbar);
+        tma_load_1d(W2, w.wih2_t, 64 * 256 * 4, &wbar);
+        tma_load_1d(W3, w.whh2_t, 64 * 256 * 4, &wbar);
+        tma_load_1d(W4, w.wl2_t, 64 * 64 * 4, &wbar);
+        tma_load_1d(W5, w.wqkv_t, 64 * NQKV * 4, &wbar);
     }
     griddep_wait();
     float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
@@ -68,6 +68,7 @@ mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict
         hT[(k4 * 4 + 0) * MID_RT + r] = v.x; hT[(k4 * 4 + 1) * MID_RT + r] = v.y;
         hT[(k4 * 4 + 2) * MID_RT + r] = v.z; hT[(k4 * 4 + 3) * MID_RT + r] = v.w;
     }
+    mbar_wait(&wbar, 0);
     __syncthreads();
     const int c = tid & 63, rp = tid >> 6;                  // column c, row pair (2rp, 2rp+1)
     // ---- phase 1: X1 = X + Y W1 + b -----------------------------------------------------------

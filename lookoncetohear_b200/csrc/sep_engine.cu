@@ -244,6 +244,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
+    CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(configure_rows_gemm());
     g_attr_done = true;
@@ -303,7 +304,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS);
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
-    CK(launch_k(false, front_kernel, dim3(T, B), dim3(256), 0, st, x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel));
+    CK(launch_k(false, front_kernel, dim3(T, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel));
     MARK("front");
     CK(launch_k(pdl, spk_gemv_kernel, dim3(FC / 32, B), dim3(256), 0, st, emb, PRE, (const float*)state, ss, e->w));
     MARK("spk_gemv");

@@ -69,15 +69,25 @@ __global__ void set_clip_base_kernel(float* state) {
 // K1 front: STFT analysis + channel regroup + causal 3x3 conv   (tfgridnet_causal.py:229-242)
 // grid (T, B), 256 threads.  x: [B][NMIC][x_len] (samples past x_len read as zero: the mod-pad and
 // look-ahead zeros of net.py:8-18,56-58).  Frames before the call start come from conv_buf.
+constexpr size_t FRONT_SMEM = (size_t)NFFT * 196 * sizeof(float);     // analysis filters, staged by TMA
+
 __global__ void __launch_bounds__(256)
 front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
              float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T,
              int pos_rel) {
+    extern __shared__ __align__(16) float wat_s[];     // [192][196]
     __shared__ float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
+    __shared__ __align__(8) unsigned long long wbar;
     griddep_launch();
-    griddep_wait();
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {                     // one bulk copy instead of a 192-deep dependent load chain
+        mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM);
+        tma_load_1d(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar);
+    }
+    griddep_wait();
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
@@ -102,19 +112,14 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
         float acc[3][NMIC];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-        // 16 independent filter loads in flight per thread (the loop is L2-latency bound otherwise)
-#pragma unroll 1
-        for (int n0 = 0; n0 < NFFT; n0 += 16) {
-            float wv[16];
+        mbar_wait(&wbar, 0);
+#pragma unroll 8
+        for (int n = 0; n < NFFT; ++n) {
+            const float wv = wat_s[n * 196 + tid];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w.wat + (n0 + u) * 196 + tid);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    acc[i][0] = fmaf(wv[u], xs[0][HOP * i + n0 + u], acc[i][0]);
-                    acc[i][1] = fmaf(wv[u], xs[1][HOP * i + n0 + u], acc[i][1]);
-                }
+            for (int i = 0; i < 3; ++i) {
+                acc[i][0] = fmaf(wv, xs[0][HOP * i + n], acc[i][0]);
+                acc[i][1] = fmaf(wv, xs[1][HOP * i + n], acc[i][1]);
             }
         }
         const int ri = tid / NF, f = tid % NF;      // rows 0..96 real, 97..193 imaginary
@@ -240,8 +245,9 @@ __global__ void kv_gather_kernel(const float* __restrict__ state, int64_t sstrid
 // append to the K/V history   (tfgridnet_causal.py:547-562, modules :354-387).
 // grid (T, B), 384 threads (12 warps = {Q,K,V} x 4 heads for the LayerNorm phase).
 constexpr int QKV_THREADS = 384;
-constexpr int QKV_PLD = 113;
-constexpr size_t QKV_SMEM = (size_t)(64 * 100 + 64 * NQKV + NF * QKV_PLD) * sizeof(float);
+constexpr int QKV_PLD = NQKV;                 // 112: a frame's projections are one contiguous 43 KB tile
+constexpr int QKV_LNP = 4 * QK_LD + 2 * V_DIM;  // staged LayerNorm params: gq | bq | gk | bk | gv | bv
+constexpr size_t QKV_SMEM = (size_t)(64 * 100 + 64 * NQKV + NF * QKV_PLD + QKV_LNP) * sizeof(float);
 
 __global__ void __launch_bounds__(QKV_THREADS)
 qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __restrict__ Qbuf,
@@ -250,22 +256,34 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
     extern __shared__ __align__(16) float sm[];
     float* Xt = sm;                      // [64][100]  k-major, rows padded to 100 (zeros)
     float* Ws = Xt + 64 * 100;           // [64][112]
-    float* P = Ws + 64 * NQKV;           // [97][113]
+    float* P = Ws + 64 * NQKV;           // [97][112]
+    float* LNP = P + NF * QKV_PLD;       // gq[584] bq[584] gk[584] bk[584] gv[1552] bv[1552]
+    __shared__ __align__(8) unsigned long long bars[2];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     griddep_launch();
-    if (pre == nullptr)
-        for (int i = tid; i < 64 * NQKV / 4; i += QKV_THREADS)  // weights: independent of the chain
-            reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wqkv_t) + i);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {                      // parameters: independent of the chain -> before the wait
+        // (the 582-float vectors are followed by 2 floats of alignment padding in the packed buffer)
+        mbar_expect_tx(&bars[0], (unsigned)(QKV_LNP * 4 + (pre == nullptr ? 64 * NQKV * 4 : 0)));
+        tma_load_1d(LNP, w.lnq_g, QK_LD * 4, &bars[0]);
+        tma_load_1d(LNP + QK_LD, w.lnq_b, QK_LD * 4, &bars[0]);
+        tma_load_1d(LNP + 2 * QK_LD, w.lnk_g, QK_LD * 4, &bars[0]);
+        tma_load_1d(LNP + 3 * QK_LD, w.lnk_b, QK_LD * 4, &bars[0]);
+        tma_load_1d(LNP + 4 * QK_LD, w.lnv_g, V_DIM * 4, &bars[0]);
+        tma_load_1d(LNP + 4 * QK_LD + V_DIM, w.lnv_b, V_DIM * 4, &bars[0]);
+        if (pre == nullptr) tma_load_1d(Ws, w.wqkv_t, 64 * NQKV * 4, &bars[0]);
+    }
     griddep_wait();
-    if (pre != nullptr) {            // projections already done by mid_kernel: just stage them
-        const float4* src = reinterpret_cast<const float4*>(pre + ((int64_t)b * T + t) * NF * NQKV);
-        for (int i = tid; i < NF * NQKV / 4; i += QKV_THREADS) {
-            const float4 v = src[i];
-            const int f = (i * 4) / NQKV, n = (i * 4) % NQKV;     // NQKV % 4 == 0: a float4 never straddles rows
-            P[f * QKV_PLD + n + 0] = v.x; P[f * QKV_PLD + n + 1] = v.y;
-            P[f * QKV_PLD + n + 2] = v.z; P[f * QKV_PLD + n + 3] = v.w;
+    if (pre != nullptr) {            // projections already done by mid_kernel: one bulk copy stages them
+        if (tid == 0) {
+            mbar_expect_tx(&bars[1], NF * NQKV * 4);
+            tma_load_1d(P, pre + ((int64_t)b * T + t) * NF * NQKV, NF * NQKV * 4, &bars[1]);
         }
+        mbar_wait(&bars[1], 0);
+        mbar_wait(&bars[0], 0);
     } else {
+    mbar_wait(&bars[0], 0);
     const float* xr = X + ((int64_t)b * T + t) * NF * CH;
     for (int i = tid; i < 100 * 16; i += QKV_THREADS) {       // float4 loads; lanes along f -> conflict-free stores
         const int c4 = i / 100, f = i % 100;
@@ -338,8 +356,8 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
         }
     }
     const float rs = rsqrtf(warp_sum(q) / (float)n + 1e-5f);
-    const float* gam = (which == 0) ? w.lnq_g : (which == 1 ? w.lnk_g : w.lnv_g);
-    const float* bet = (which == 0) ? w.lnq_b : (which == 1 ? w.lnk_b : w.lnv_b);
+    const float* gam = LNP + (which == 0 ? 0 : (which == 1 ? 2 * QK_LD : 4 * QK_LD));
+    const float* bet = LNP + (which == 0 ? QK_LD : (which == 1 ? 3 * QK_LD : 4 * QK_LD + V_DIM));
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const long long pos = hdr->pos;
     const int ld = (which == 2) ? V_DIM : QK_LD;
@@ -358,7 +376,7 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
     {
         int f = f0, e2 = e0;
         for (int i = lane; i < n; i += 32) {
-            const float v = (P[f * QKV_PLD + col0 + e2] - mu) * rs * __ldg(gam + i) + __ldg(bet + i);
+            const float v = (P[f * QKV_PLD + col0 + e2] - mu) * rs * gam[i] + bet[i];
             if (dst0) dst0[i] = v;
             if (dst1) dst1[i] = v;
             e2 += de; f += df;
@@ -482,7 +500,7 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
 // K4c attention output: Linear(64->64) + PReLU + LayerNorm over (F, C) + residual
 // (tfgridnet_causal.py:583-588); for block 0 the speaker gate that the reference applies to the
 // input of block 1 (:250-251) is folded into this epilogue.  grid (T, B), 256 threads.
-constexpr size_t AOUT_SMEM = (size_t)(64 * 100 + 64 * 64 + NF * 64) * sizeof(float);
+constexpr size_t AOUT_SMEM = (size_t)(64 * 100 + 64 * 64 + NF * 64 + 4 * FC) * sizeof(float);   // + gamma, beta, X row, gate
 
 __global__ void __launch_bounds__(256)
 attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float* __restrict__ state,
@@ -493,11 +511,29 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     float* Zt = sm;                 // [64][100]
     float* Ws = Zt + 64 * 100;      // [64][64]
     float* P = Ws + 64 * 64;        // [97][64]
+    float* Gs = P + NF * 64;        // LN gamma  [6208]
+    float* Bs = Gs + FC;            // LN beta
+    float* Xr = Bs + FC;            // the frame's rows of X (residual)
+    float* Gt = Xr + FC;            // speaker gate (block 0 only)
+    __shared__ __align__(8) unsigned long long bars[2];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    float* xr = X + ((int64_t)b * T + t) * NF * CH;
+    const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
     griddep_launch();
-    for (int i = tid; i < 64 * 64 / 4; i += 256)
-        reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(w.wp_t) + i);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {                 // parameters: before the dependency wait
+        mbar_expect_tx(&bars[0], (64 * 64 + 2 * FC) * 4);
+        tma_load_1d(Ws, w.wp_t, 64 * 64 * 4, &bars[0]);
+        tma_load_1d(Gs, w.lnp_g, FC * 4, &bars[0]);
+        tma_load_1d(Bs, w.lnp_b, FC * 4, &bars[0]);
+    }
     griddep_wait();
+    if (tid == 0) {                 // chain data: the residual rows and (block 0) the gate
+        mbar_expect_tx(&bars[1], (apply_gate ? 2 : 1) * FC * 4);
+        tma_load_1d(Xr, xr, FC * 4, &bars[1]);
+        if (apply_gate) tma_load_1d(Gt, gate, FC * 4, &bars[1]);
+    }
     if (nsplit == 1) {
         const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
         for (int i = tid; i < 100 * 16; i += 256) {
@@ -541,6 +577,7 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
             Zt[(k + 2) * 100 + f] = o.z; Zt[(k + 3) * 100 + f] = o.w;
         }
     }
+    mbar_wait(&bars[0], 0);
     __syncthreads();
     const float slope = __ldg(w.slopes + 3);
     for (int it = tid; it < 25 * 16; it += 256) {
@@ -583,17 +620,16 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     float q = 0.f;
     for (int i = tid; i < FC; i += 256) { const float d = P[i] - mu; q += d * d; }
     const float rs = rsqrtf(block_sum(q, red) * (1.f / FC) + 1e-5f);
-    float* xr = X + ((int64_t)b * T + t) * NF * CH;
-    const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
+    mbar_wait(&bars[1], 0);
     for (int i = tid; i < FC / 4; i += 256) {
-        float4 x4 = reinterpret_cast<float4*>(xr)[i];
+        float4 x4 = reinterpret_cast<const float4*>(Xr)[i];
         const float4 p4 = reinterpret_cast<const float4*>(P)[i];
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.lnp_g) + i);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.lnp_b) + i);
+        const float4 g4 = reinterpret_cast<const float4*>(Gs)[i];
+        const float4 b4 = reinterpret_cast<const float4*>(Bs)[i];
         x4.x += (p4.x - mu) * rs * g4.x + b4.x; x4.y += (p4.y - mu) * rs * g4.y + b4.y;
         x4.z += (p4.z - mu) * rs * g4.z + b4.z; x4.w += (p4.w - mu) * rs * g4.w + b4.w;
         if (apply_gate) {
-            const float4 t4 = reinterpret_cast<const float4*>(gate)[i];
+            const float4 t4 = reinterpret_cast<const float4*>(Gt)[i];
             x4.x *= t4.x; x4.y *= t4.y; x4.z *= t4.z; x4.w *= t4.w;
         }
         reinterpret_cast<float4*>(xr)[i] = x4;
@@ -604,19 +640,39 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
 // K5 back: causal 3x3 transposed conv (64 -> 4) + Re/Im regroup + synthesis filterbank +
 // overlap-add   (tfgridnet_causal.py:256-273; net.py:61 drops the look-ahead tail).
 // grid (T, B), 256 threads.  y: [B][NSRC][y_len], frame t writes samples 128 t .. 128 t + 127.
+// The frames of X (4 x 24.8 KB, contiguous) arrive by TMA; the synthesis filterbank (149 KB) is then
+// streamed by TMA in two halves through the same shared-memory region once the deconv is done.
 // The last CTA to finish advances the state header (pos += T, ncalls += 1).
-constexpr size_t BACK_SMEM = (size_t)(4 * 99 * 64 + 2 * NSRC * NROW + NSRC * HOP + NSRC * LOOKAHEAD) * sizeof(float);
+constexpr int BACK_WS_HALF = NROW / 2;      // 97 filter rows per half
+constexpr size_t BACK_SMEM = (size_t)(4 * 99 * 64 + 2 * NSRC * NROW + NSRC * NFFT) * sizeof(float);
+static_assert(BACK_WS_HALF * NFFT <= 4 * 99 * 64, "filter half must fit in the frame region");
 
 __global__ void __launch_bounds__(256)
 back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
             int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel) {
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]
+    float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]; later: filter halves
     float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
-    float* outs = R + 2 * NSRC * NROW;    // [2 ears][128]
-    float* tails = outs + NSRC * HOP;     // [2 ears][64]  w_{t-1}[128..191]
+    float* wacc = R + 2 * NSRC * NROW;    // [2 ears][192] partial synthesis sums
+    __shared__ __align__(8) unsigned long long bars[3];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     griddep_launch();
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    // zero the frequency padding rows (0 and 98) of every slot and whole slots that stay empty
+    for (int i = tid; i < 4 * 99 * 64; i += 256) {
+        const int slot = i / (99 * 64), r = (i / 64) % 99;
+        const int tt = t - 3 + slot;
+        if (r == 0 || r == 98 || tt < -2) Xs[i] = 0.f;
+    }
+    float wr[2][36];
+    {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 36; ++k) wr[u][k] = __ldg(w.wd + (lane + 32 * u) * 36 + k);
+    }
+    __syncthreads();
     griddep_wait();
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
@@ -626,26 +682,22 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
     const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
     float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
-
-    for (int i = tid; i < 4 * 99 * 16; i += 256) {          // float4 granularity
-        const int slot = i / (99 * 16), r = (i / 16) % 99, c4 = i % 16;
-        const int tt = t - 3 + slot, f = r - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f >= 0 && f < NF) {
-            if (tt >= 0) v = *reinterpret_cast<const float4*>(X + (((int64_t)b * T + tt) * NF + f) * CH + c4 * 4);
-            else if (tt >= -2) v = *reinterpret_cast<const float4*>(db + (2 + tt) * FC + f * CH + c4 * 4);
+    if (tid == 0) {
+        fence_proxy_async();                // (zero-fill above went through the generic proxy)
+        int nfr = 0;
+        for (int slot = 0; slot < 4; ++slot) nfr += (t - 3 + slot >= -2) ? 1 : 0;
+        mbar_expect_tx(&bars[0], nfr * FC * 4);
+        for (int slot = 0; slot < 4; ++slot) {
+            const int tt = t - 3 + slot;
+            if (tt < -2) continue;
+            const float* src = (tt >= 0) ? X + ((int64_t)b * T + tt) * FC : db + (2 + tt) * FC;
+            tma_load_1d(Xs + (slot * 99 + 1) * 64, src, FC * 4, &bars[0]);
         }
-        reinterpret_cast<float4*>(Xs)[i] = v;
     }
-    __syncthreads();
+    mbar_wait(&bars[0], 0);
     // deconv for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
     {
         const int warp = tid >> 5, lane = tid & 31;
-        float wr[2][36];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int k = 0; k < 36; ++k) wr[u][k] = __ldg(w.wd + (lane + 32 * u) * 36 + k);
         for (int fi = (t >= 1 ? 0 : 1); fi < 2; ++fi) {
             for (int f = warp; f < NF; f += 8) {
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -673,44 +725,54 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
         if (t == 0)
             for (int i = tid; i < NSRC * NROW; i += 256) R[i] = ib[i];
     }
-    __syncthreads();
-    // synthesis + overlap-add: out[n] = w_t[n] + w_{t-1}[128 + n] (n < 64)
-    for (int i = tid; i < NSRC * NFFT; i += 256) {
-        const int ear = i / NFFT, n = i % NFFT;
-        const int fi = (n < HOP) ? 1 : 0;
-        const float* rr = R + (fi * NSRC + ear) * NROW;
-        float acc = 0.f;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 192; r0 += 16) {               // 16 filter loads in flight
-            float wv[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w.ws + (r0 + u) * NFFT + n);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) acc = fmaf(rr[r0 + u], wv[u], acc);
+    // next deconv tails come straight from the staged frames
+    if (T == 1) {
+        for (int i = tid; i < FC / 4; i += 256) {
+            reinterpret_cast<float4*>(db_next)[i] = reinterpret_cast<const float4*>(Xs + (2 * 99 + 1) * 64)[i];       // frame -1
+            reinterpret_cast<float4*>(db_next + FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];  // frame 0
         }
-        acc = fmaf(rr[192], __ldg(w.ws + 192 * NFFT + n), acc);
-        acc = fmaf(rr[193], __ldg(w.ws + 193 * NFFT + n), acc);
-        if (n < HOP) outs[ear * HOP + n] = acc;
-        else tails[ear * LOOKAHEAD + (n - HOP)] = acc;
+    } else if (t >= T - 2) {
+        for (int i = tid; i < FC / 4; i += 256)
+            reinterpret_cast<float4*>(db_next + (t - (T - 2)) * FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];
+    }
+    __syncthreads();                        // R complete; nobody reads the frame region any more
+    // synthesis: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}; filters streamed in two halves
+    float part[2] = {0.f, 0.f};             // this thread's outputs: item = tid and tid + 256 of (ear, n)
+    for (int half = 0; half < 2; ++half) {
+        if (tid == 0) {
+            fence_proxy_async();            // the region was read/written through the generic proxy until now
+            mbar_expect_tx(&bars[1 + half], BACK_WS_HALF * NFFT * 4);
+            tma_load_1d(Xs, w.ws + (int64_t)half * BACK_WS_HALF * NFFT, BACK_WS_HALF * NFFT * 4, &bars[1 + half]);
+        }
+        mbar_wait(&bars[1 + half], 0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int item = tid + 256 * u;
+            if (item < NSRC * NFFT) {
+                const int ear = item / NFFT, n = item % NFFT;
+                const float* rr = R + (((n < HOP) ? 1 : 0) * NSRC + ear) * NROW + half * BACK_WS_HALF;
+                float acc = part[u];
+#pragma unroll 8
+                for (int r = 0; r < BACK_WS_HALF; ++r) acc = fmaf(rr[r], Xs[r * NFFT + n], acc);
+                part[u] = acc;
+            }
+        }
+        __syncthreads();                    // everybody is done with this half before it is overwritten
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int item = tid + 256 * u;
+        if (item < NSRC * NFFT) wacc[item] = part[u];
     }
     __syncthreads();
     for (int i = tid; i < NSRC * HOP; i += 256) {
         const int ear = i / HOP, n = i % HOP;
         const int s = HOP * t + n + soff;
         if (s < y_len) {
-            float v = outs[i];
-            if (n < LOOKAHEAD) v += tails[ear * LOOKAHEAD + n];
+            float v = wacc[ear * NFFT + n];
+            if (n < LOOKAHEAD) v += wacc[ear * NFFT + HOP + n];     // overlap-add of the previous frame's tail
             y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
         }
-    }
-    // next tails
-    if (T == 1) {
-        for (int i = tid; i < FC; i += 256) {
-            db_next[i] = Xs[(2 * 99 + 1) * 64 + i];            // frame -1 (slot 2), rows 1..97 contiguous
-            db_next[FC + i] = Xs[(3 * 99 + 1) * 64 + i];       // frame 0
-        }
-    } else if (t >= T - 2) {
-        for (int i = tid; i < FC; i += 256) db_next[(t - (T - 2)) * FC + i] = Xs[(3 * 99 + 1) * 64 + i];
     }
     if (t == T - 1)
         for (int i = tid; i < NSRC * NROW; i += 256) ib_next[i] = R[NSRC * NROW + i];
