@@ -373,6 +373,7 @@ def profile_chain(net, x_dev, emb, dev, cpc, iters=20):
     """Times every kernel of the chain with CUDA events (l2h_sep_profile) -> {name: {ms_mean, ms_total}}."""
     from lookoncetohear_b200 import _cabi
     L = _cabi.lib()
+    net._sync_weights(dev)
     st = net.init_buffers(1, dev)
     ws, _ = net._workspace(dev, 1, cpc)
     n = ctypes.c_int32()

@@ -1,0 +1,86 @@
+"""Parity at the shapes of the remaining BASELINE.json configurations, through size-independent
+properties where the oracle cannot run the full size in seconds:
+  configs[2]  offline batched separation (here fp32; the bf16/tcgen05 variant is not built yet)
+  configs[3]  batched enrollment
+  configs[4]  batched streaming, many independent streams advancing one hop per step
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lookoncetohear_b200 import EmbedTFGridNet, Net, synth
+from oracle import restate as rs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def sep(tsh_params, dev):
+    torch.manual_seed(0)
+    net = Net(**tsh_params).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net.to(dev), sd
+
+
+def test_offline_batch_of_4s_clips(sep, dev):
+    """configs[2] shape per stream (4 s, T = 500), batch 24 (the forward splits it into independent
+    launches): every stream must equal its own single-stream run (batch independence), and two of
+    them are checked against the oracle."""
+    net, sd = sep
+    B = 24
+    x, tgt = synth.mixture(B, 64000, seed0=400)
+    e = synth.embedding(B, seed0=500)
+    with torch.no_grad():
+        y = net(x.to(dev), e.to(dev)).cpu()
+        for b in (0, 7, 23):
+            yb = net(x[b:b + 1].to(dev), e[b:b + 1].to(dev)).cpu()
+            assert rs.rel_l2(y[b:b + 1], yb) < 1e-5
+    torch.set_num_threads(8)
+    for b in (3, 17):
+        y_ref = rs.sep_forward(sd, x[b:b + 1], e[b:b + 1])
+        assert rs.rel_l2(y[b:b + 1], y_ref) <= 1e-3
+        d = (rs.si_sdr(y[b:b + 1], tgt[b:b + 1]) - rs.si_sdr(y_ref, tgt[b:b + 1])).abs().max()
+        assert float(d) <= 0.1
+
+
+def test_batched_streaming_many_streams(sep, dev):
+    """configs[4] per-GPU shape: 256 independent streams, one 8 ms hop per step.  60 steps (the ring
+    wraps); three streams are compared with the oracle, all with the buffered (whole-clip) run."""
+    net, sd = sep
+    B, T = 256, 60
+    x, _ = synth.mixture(B, 128 * T, seed0=600)
+    e = synth.embedding(B, seed0=700)
+    xd, ed = x.to(dev), e[:, 0].to(dev)
+    with torch.no_grad():
+        y_stream = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+        y_whole = net(xd, e.to(dev)).cpu()
+    assert rs.rel_l2(y_stream, y_whole) < 1e-4
+    for b in (0, 101, 255):
+        y_ref = rs.sep_forward(sd, x[b:b + 1], e[b:b + 1])
+        assert rs.rel_l2(y_stream[b:b + 1], y_ref) <= 1e-3
+
+
+def test_batched_enrollment(embed_params, dev):
+    """configs[3] shape per utterance (5 s), batch 6: batch independence + oracle on one utterance
+    of a shorter length (the CPU oracle needs minutes for a 5 s full-attention clip)."""
+    torch.manual_seed(0)
+    net = EmbedTFGridNet(**embed_params).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(dev)
+    x = synth.enrollment(6, 80000, seed0=800)
+    with torch.no_grad():
+        full = net(x.to(dev)).cpu()
+        one = net(x[4:5].to(dev)).cpu()
+    assert torch.isfinite(full).all()
+    assert rs.rel_l2(full[4:5], one) < 1e-5
+    xs = synth.enrollment(2, 16000, seed0=900)
+    with torch.no_grad():
+        o = net(xs.to(dev)).cpu()
+    r = rs.embed_forward(sd, xs)
+    assert rs.rel_l2(o, r) <= 1e-3 and float(F.cosine_similarity(o, r).min()) >= 0.9999
