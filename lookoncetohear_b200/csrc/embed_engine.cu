@@ -268,6 +268,7 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
     if (rows * 2 > 0x7fffffff) return fail(1, "batch too large for one call; split it (l2h_embed_max_batch)");
     if (!e->attrs) {
         CK(configure_rows_gemm());
+        CK(configure_lstm());
         CK(cudaFuncSetAttribute(eattn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EAOUT_SMEM));
         e->attrs = true;
     }

@@ -298,14 +298,196 @@ lstm_rec2_kernel(const LstmArgs a) {
     }
 }
 
+// ---- variant 3 (default): 128 threads, thread = (hidden unit j, k-half) --------------------------
+// Measured on B200 (profiles/r01c_lstm_microbench.txt): a broadcast LDS.128 still costs 4 LSU passes, so
+// the 16 x 8-warp broadcasts of h per step of variant 1 are the step's largest cost (340 ns/step; 230 ns
+// with every MUFU, copy and store removed).  Here a thread owns all FOUR gate rows of unit j over HALF
+// of k: 8 LDS.128 feed 64 FFMA2 (4x the FMAs per shared-memory byte of variant 1), the two k-halves
+// meet with one shuffle-add per gate, and both lanes then hold all four pre-activations, so the gate
+// exchange needs only two more shuffles.
+// PRE = true: the whole input projection of the sequence (L x 1 KB) is brought in up front by TMA bulk
+// copies (one per step row) -- no per-step async bookkeeping at all; used when it fits (short L).
+// PRE = false: 8-stage cp.async ring refilled four rows (one group) at a time.
+constexpr int L3_STAGES = 8;
+
+template <int NSEQ, bool PRE>
+__global__ void __launch_bounds__(128, PRE ? 1 : 2)
+lstm_rec3_kernel(const LstmArgs a) {
+    extern __shared__ __align__(16) float gdyn[];            // PRE: [NSEQ][L][256]
+    __shared__ __align__(16) float hbuf[2][NSEQ][64];
+    __shared__ __align__(16) float gring[PRE ? 1 : L3_STAGES][PRE ? 1 : NSEQ][PRE ? 4 : 256];
+    __shared__ __align__(8) unsigned long long gbar;
+
+    griddep_launch();
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const int seq0 = blockIdx.x * NSEQ;
+    const int j = tid >> 1, kh = tid & 1;
+
+    float2 w[4][16];                      // rows j*4+q, k in [32 kh, 32 kh + 32)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4* wp = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + j * 4 + q) * 64 + 32 * kh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 t = __ldg(wp + k);
+            w[q][2 * k] = make_float2(t.x, t.y);
+            w[q][2 * k + 1] = make_float2(t.z, t.w);
+        }
+    }
+    if (PRE && tid == 0) { mbar_init(&gbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    griddep_wait();
+
+    const bool own_out = (a.out_outer_stride | a.out_inner_stride | a.out_step_stride) != 0;
+    const int64_t o_step = (own_out ? a.out_step_stride : a.step_stride) * a.out_ld;
+    const int sgn = (dir == 0) ? 1 : -1;
+    const int first = (dir == 0) ? 0 : a.L - 1;
+    const int64_t g_step = a.step_stride * a.gx_ld * sgn;
+
+    float c[NSEQ];
+    bool valid[NSEQ];
+    float* outp[NSEQ];
+    int64_t hc[NSEQ];
+    const float* grow[NSEQ];              // &gx[row(seq, first)][dir*256]
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) {
+        const int seq = seq0 + s;
+        valid[s] = seq < a.nseq;
+        const int sq = valid[s] ? seq : 0;
+        const int so = sq / a.inner_count, si = sq % a.inner_count;
+        const int64_t gb = (int64_t)so * a.outer_stride + (int64_t)si * a.inner_stride;
+        const int64_t ob = own_out ? (int64_t)so * a.out_outer_stride + (int64_t)si * a.out_inner_stride : gb;
+        grow[s] = a.gx + (gb + (int64_t)first * a.step_stride) * a.gx_ld + dir * 256;
+        outp[s] = a.out + ob * a.out_ld + (int64_t)first * o_step + dir * 64 + j;
+        hc[s] = (int64_t)so * a.hc_outer_stride + (int64_t)si * 64 + j;
+        c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
+        if (kh == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
+    }
+
+    if (PRE) {
+        // one 1 KB bulk copy per (sequence, step): row of iteration `it` lands at gdyn[s][it][:]
+        int nrows = 0;
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) nrows += valid[s] ? a.L : 0;
+        if (tid == 0) mbar_expect_tx(&gbar, (unsigned)nrows * 1024u);
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s)
+            if (valid[s])
+                for (int it = tid; it < a.L; it += 128)
+                    tma_load_1d(gdyn + ((int64_t)s * a.L + it) * 256, grow[s] + (int64_t)it * g_step, 1024, &gbar);
+        mbar_wait(&gbar, 0);
+    }
+    // ring refill: group g = rows 4g .. 4g+3 -> stages (g % 2)*4 .. +3 ; 64 x 16 B chunks per row
+    auto issue_group = [&](int g) {
+        if (!PRE) {
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int idx = tid + 128 * u, r = idx >> 6, chunk = idx & 63;
+                    const int it = 4 * g + r;
+                    if (valid[s] && it < a.L)
+                        cp_async16(&gring[(g % 2) * 4 + r][s][chunk * 4], grow[s] + (int64_t)it * g_step + chunk * 4);
+                }
+            }
+            cp_async_commit();
+        }
+    };
+    if (!PRE) {
+        issue_group(0);
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    const float LOG2E = 1.4426950408889634f;
+    const float S0 = kh ? -2.f * LOG2E : -LOG2E, A0 = kh ? 2.f : 1.f, B0 = kh ? -1.f : 0.f;
+
+    int cur = 0;
+    for (int it = 0; it < a.L; ++it) {
+        if (!PRE && (it & 3) == 0) issue_group((it >> 2) + 1);      // overwrites the group consumed 4 steps ago
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            const float* gr = PRE ? gdyn + ((int64_t)s * a.L + it) * 256 : &gring[it % L3_STAGES][s][0];
+            const float2 g2 = *reinterpret_cast<const float2*>(gr + j * 4 + 2 * kh);   // this lane adds gx of gates 2kh, 2kh+1
+            const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][s][32 * kh]);
+            float2 acc[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q][0] = make_float2(0.f, 0.f); acc[q][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 h4 = hp[k];
+                const float2 hA = make_float2(h4.x, h4.y), hB = make_float2(h4.z, h4.w);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q][0] = ffma2(w[q][2 * k], hA, acc[q][0]);
+                    acc[q][1] = ffma2(w[q][2 * k + 1], hB, acc[q][1]);
+                }
+            }
+            float p[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float gadd = ((q >> 1) == kh) ? ((q & 1) ? g2.y : g2.x) : 0.f;
+                const float t = ((acc[q][0].x + acc[q][0].y) + (acc[q][1].x + acc[q][1].y)) + gadd;
+                p[q] = t + __shfl_xor_sync(0xffffffffu, t, 1);
+            }
+            // lane kh = 0 activates (i, f); lane kh = 1 activates (g, o)
+            const float x0 = kh ? p[2] : p[0], x1 = kh ? p[3] : p[1];
+            const float v0 = __fdividef(A0, 1.f + ex2_ftz(S0 * x0)) + B0;
+            const float v1 = __fdividef(1.f, 1.f + ex2_ftz(-LOG2E * x1));
+            const float og = __shfl_xor_sync(0xffffffffu, v0, 1);
+            const float oo = __shfl_xor_sync(0xffffffffu, v1, 1);
+            c[s] = v1 * c[s] + v0 * og;                  // meaningful on kh == 0 lanes: f*c + i*g
+            const float h = oo * (__fdividef(2.f, 1.f + ex2_ftz(-2.f * LOG2E * c[s])) - 1.f);
+            if (kh == 0) {
+                hbuf[cur ^ 1][s][j] = h;
+                if (valid[s]) *outp[s] = h;
+            }
+            outp[s] += sgn * o_step;
+        }
+        cur ^= 1;
+        if (!PRE && (it & 3) == 3) cp_async_wait<0>();    // the next four rows (issued 4 steps ago) have landed
+        __syncthreads();
+    }
+    if (a.h_state != nullptr) {
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            if (valid[s] && kh == 0) {
+                a.h_state[hc[s]] = hbuf[cur][s][j];
+                a.c_state[hc[s]] = c[s];
+            }
+        }
+    }
+}
+
 inline int lstm_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("L2H_LSTM_V"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("L2H_LSTM_V"); v = e ? atoi(e) : 3; }
     return v;
+}
+
+inline cudaError_t configure_lstm() {
+    cudaError_t e = cudaFuncSetAttribute(lstm_rec3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
 }
 
 inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st, bool pdl = false) {
     if (a.nseq <= 0 || a.L <= 0) return cudaErrorInvalidValue;
+    if (lstm_variant() == 3) {
+        const int ctas1 = a.nseq * a.ndir;
+        if (ctas1 <= 148 && (size_t)a.L * 1024 <= 200 * 1024) {      // latency mode: one sequence per CTA, preloaded
+            return launch_k(pdl, lstm_rec3_kernel<1, true>, dim3(a.nseq, a.ndir), dim3(128), (size_t)a.L * 1024, st, a);
+        }
+        int per = 1;
+        while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
+        dim3 grid((a.nseq + per - 1) / per, a.ndir);
+        switch (per) {
+            case 1: return launch_k(pdl, lstm_rec3_kernel<1, false>, grid, dim3(128), 0, st, a);
+            case 2: return launch_k(pdl, lstm_rec3_kernel<2, false>, grid, dim3(128), 0, st, a);
+            default: return launch_k(pdl, lstm_rec3_kernel<4, false>, grid, dim3(128), 0, st, a);
+        }
+    }
     if (lstm_variant() == 2) {
         int per = 1;
         while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;

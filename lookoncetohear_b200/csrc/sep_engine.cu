@@ -247,6 +247,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(configure_rows_gemm());
+    CK(configure_lstm());
     g_attr_done = true;
     return 0;
 }

@@ -82,7 +82,21 @@ int main() {
     auto rep = [&](const char* name, float ms) { printf("%-46s %8.1f ns/step\n", name, 1e6f * ms / L); };
     rep("v1 lstm_rec_kernel<1> (256 thr, 2 dirs on 2 SMs)", time_it([&] { lstm_rec_kernel<1><<<dim3(1, 2), 256>>>(a); }));
     rep("v2 lstm_rec2_kernel<1> (128 thr x 2 rows)", time_it([&] { lstm_rec2_kernel<1><<<dim3(1, 2), 128>>>(a); }));
+    rep("v3 lstm_rec3_kernel<1,ring> (128 thr, unit x k-half)", time_it([&] { lstm_rec3_kernel<1, false><<<dim3(1, 2), 128>>>(a); }));
+    {
+        cudaFuncSetAttribute(lstm_rec3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        LstmArgs b = a; b.L = 194; b.outer_stride = 194;
+        float ms = time_it([&] { lstm_rec3_kernel<1, true><<<dim3(1, 2), 128, 194 * 1024>>>(b); });
+        printf("%-46s %8.1f ns/step (L=194, incl. preload + launch)\n", "v3 lstm_rec3_kernel<1,preload>", 1e6f * ms / 194);
+        b.L = 97; b.outer_stride = 97;
+        ms = time_it([&] { lstm_rec3_kernel<1, true><<<dim3(1, 2), 128, 97 * 1024>>>(b); });
+        printf("%-46s %8.2f us per launch (L=97, both directions)\n", "v3 preload, the T=1 intra launch", 1e3f * ms);
+        LstmArgs c1 = a; c1.L = 97; c1.outer_stride = 97;
+        ms = time_it([&] { lstm_rec_kernel<1><<<dim3(1, 2), 256>>>(c1); });
+        printf("%-46s %8.2f us per launch (L=97, both directions)\n", "v1, the T=1 intra launch", 1e3f * ms);
+    }
     a.nseq = 4;  a.outer_stride = L / 4; a.L = L / 4;
+    { float ms = time_it([&] { lstm_rec3_kernel<4, false><<<dim3(1, 2), 128>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v3 NSEQ=4", 1e6f * ms / (L / 4)); }
     { float ms = time_it([&] { lstm_rec_kernel<4><<<dim3(1, 2), 256>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v1 NSEQ=4", 1e6f * ms / (L / 4)); }
     { float ms = time_it([&] { lstm_rec2_kernel<4><<<dim3(1, 2), 128>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v2 NSEQ=4", 1e6f * ms / (L / 4)); }
     rep("exp: full (ring, stg, tanh, act, bar0)", time_it([&] { exp_kernel<true, true, true, true, true><<<1, 256>>>(gx, out, whh, L); }));
