@@ -80,6 +80,17 @@ L2H_DEVINL void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// A single large bulk copy is served slowly (measured: 150 KB by one instruction ~ 10 us on one SM); many
+// 2 KB copies issued by different threads keep enough requests in flight to run at L2 speed.
+// Called by ALL threads of the CTA (each issues its share); the caller arms the barrier with the byte total.
+L2H_DEVINL void tma_load_split(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar,
+                               int tid, int nthreads) {
+    constexpr unsigned CH = 2048;
+    for (unsigned off = (unsigned)tid * CH; off < bytes; off += (unsigned)nthreads * CH) {
+        const unsigned n = (bytes - off < CH) ? (bytes - off) : CH;
+        tma_load_1d(reinterpret_cast<char*>(dst_smem) + off, reinterpret_cast<const char*>(src_gmem) + off, n, bar);
+    }
+}
 // order earlier generic-proxy accesses of shared memory before later async-proxy (TMA) writes to it
 L2H_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 L2H_DEVINL void mbar_wait(unsigned long long* bar, unsigned phase) {
@@ -118,6 +129,22 @@ inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// same, as thread-block clusters of `cluster` CTAs (distributed shared memory between them)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster(bool pdl, dim3 cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster.x; attr[0].val.clusterDim.y = cluster.y; attr[0].val.clusterDim.z = cluster.z;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 }  // namespace l2h

@@ -42,14 +42,13 @@ mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict
     // ---- weights -> smem: five TMA bulk copies (independent of the chain, so issued before the wait)
     if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&wbar, (128 * 64 + 64 * 256 + 64 * 256 + 64 * 64 + 64 * NQKV) * 4);
-        tma_load_1d(W1, w.wl1_t, 128 * 64 * 4, &wbar);
-        tma_load_1d(W2, w.wih2_t, 64 * 256 * 4, &wbar);
-        tma_load_1d(W3, w.whh2_t, 64 * 256 * 4, &wbar);
-        tma_load_1d(W4, w.wl2_t, 64 * 64 * 4, &wbar);
-        tma_load_1d(W5, w.wqkv_t, 64 * NQKV * 4, &wbar);
-    }
+    if (tid == 0) mbar_expect_tx(&wbar, (128 * 64 + 64 * 256 + 64 * 256 + 64 * 64 + 64 * NQKV) * 4);
+    __syncthreads();
+    tma_load_split(W1, w.wl1_t, 128 * 64 * 4, &wbar, tid, 256);
+    tma_load_split(W2, w.wih2_t, 64 * 256 * 4, &wbar, tid, 256);
+    tma_load_split(W3, w.whh2_t, 64 * 256 * 4, &wbar, tid, 256);
+    tma_load_split(W4, w.wl2_t, 64 * 64 * 4, &wbar, tid, 256);
+    tma_load_split(W5, w.wqkv_t, 64 * NQKV * 4, &wbar, tid, 256);
     griddep_wait();
     float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
     float* hst = sb + BK_H;

@@ -212,10 +212,7 @@ struct Workspace {
 // few frames in flight -> split every head's 50-row window over several CTAs
 static int attn_splits(int B, int T) {
     const int ctas = B * T * NHEAD;
-    if (ctas >= 148) return 1;
-    if (ctas * 2 >= 148) return 2;
-    if (ctas * 5 >= 148) return 5;
-    return 10;
+    return (ctas * ATT_CL <= 296) ? ATT_CL : 1;      // 8-CTA clusters while they all fit in one wave
 }
 
 static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
@@ -231,7 +228,7 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.KALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * QK_LD : 0);
     ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
     ws.PRE = alloc((int64_t)B * FC);
-    ws.PART = alloc(attn_splits(B, T) > 1 ? (int64_t)B * T * NHEAD * attn_splits(B, T) * PART_LD : 0);
+    ws.PART = alloc(0);      // (split-attention partials now live in distributed shared memory)
     ws.QKVRAW = alloc(T == 1 ? (int64_t)B * NF * NQKV : 0);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
     ws.total = cur;
@@ -369,11 +366,16 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
                     (const float*)(fused_mid ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T));
         MARK("qkv");
-        CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD * nsplit, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
-                    (const float*)VALL, (const float*)state, ss, b, Z, PART, nsplit, T));
+        if (nsplit > 1) {
+            CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
+                              (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T));
+        } else {
+            CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
+                        (const float*)VALL, (const float*)state, ss, b, Z, PART, 1, T));
+        }
         MARK("attn");
         CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
-                    (b == 0 && e->n_blocks > 1) ? 1 : 0, (const float*)PART, nsplit, T));
+                    (b == 0 && e->n_blocks > 1) ? 1 : 0, (const float*)PART, 1, T));
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }

@@ -2,6 +2,8 @@
 // Reference: /root/reference/src/models/tfgridnet_realtime/tfgridnet_causal.py (cited per kernel).
 // Activations are [B, T, F=97, C=64] fp32 rows of 256 B.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "sep_layout.h"
 
@@ -83,10 +85,9 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
     __syncthreads();
-    if (tid == 0) {                     // one bulk copy instead of a 192-deep dependent load chain
-        mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM);
-        tma_load_1d(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar);
-    }
+    if (tid == 0) mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM);
+    __syncthreads();
+    tma_load_split(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar, tid, 256);     // 74 bulk copies in flight
     griddep_wait();
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
@@ -263,23 +264,21 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
     griddep_launch();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
-    if (tid == 0) {                      // parameters: independent of the chain -> before the wait
-        // (the 582-float vectors are followed by 2 floats of alignment padding in the packed buffer)
-        mbar_expect_tx(&bars[0], (unsigned)(QKV_LNP * 4 + (pre == nullptr ? 64 * NQKV * 4 : 0)));
-        tma_load_1d(LNP, w.lnq_g, QK_LD * 4, &bars[0]);
-        tma_load_1d(LNP + QK_LD, w.lnq_b, QK_LD * 4, &bars[0]);
-        tma_load_1d(LNP + 2 * QK_LD, w.lnk_g, QK_LD * 4, &bars[0]);
-        tma_load_1d(LNP + 3 * QK_LD, w.lnk_b, QK_LD * 4, &bars[0]);
-        tma_load_1d(LNP + 4 * QK_LD, w.lnv_g, V_DIM * 4, &bars[0]);
-        tma_load_1d(LNP + 4 * QK_LD + V_DIM, w.lnv_b, V_DIM * 4, &bars[0]);
-        if (pre == nullptr) tma_load_1d(Ws, w.wqkv_t, 64 * NQKV * 4, &bars[0]);
+    // parameters: independent of the chain -> before the wait
+    // (the 582-float vectors are followed by 2 floats of alignment padding in the packed buffer)
+    if (tid == 0) mbar_expect_tx(&bars[0], (unsigned)(QKV_LNP * 4 + (pre == nullptr ? 64 * NQKV * 4 : 0)));
+    __syncthreads();
+    if (tid < 6) {
+        const float* src = tid == 0 ? w.lnq_g : tid == 1 ? w.lnq_b : tid == 2 ? w.lnk_g : tid == 3 ? w.lnk_b : tid == 4 ? w.lnv_g : w.lnv_b;
+        float* dst = LNP + (tid < 4 ? tid * QK_LD : 4 * QK_LD + (tid - 4) * V_DIM);
+        tma_load_1d(dst, src, (tid < 4 ? QK_LD : V_DIM) * 4, &bars[0]);
     }
+    if (pre == nullptr) tma_load_split(Ws, w.wqkv_t, 64 * NQKV * 4, &bars[0], tid, QKV_THREADS);
     griddep_wait();
-    if (pre != nullptr) {            // projections already done by mid_kernel: one bulk copy stages them
-        if (tid == 0) {
-            mbar_expect_tx(&bars[1], NF * NQKV * 4);
-            tma_load_1d(P, pre + ((int64_t)b * T + t) * NF * NQKV, NF * NQKV * 4, &bars[1]);
-        }
+    if (pre != nullptr) {            // projections already done by mid_kernel: bulk copies stage them
+        if (tid == 0) mbar_expect_tx(&bars[1], NF * NQKV * 4);
+        __syncthreads();
+        tma_load_split(P, pre + ((int64_t)b * T + t) * NF * NQKV, NF * NQKV * 4, &bars[1], tid, QKV_THREADS);
         mbar_wait(&bars[1], 0);
         mbar_wait(&bars[0], 0);
     } else {
@@ -496,6 +495,129 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
     if (nsplit > 1 && tid == 0) { pr[V_DIM] = mx; pr[V_DIM + 1] = lsum; }
 }
 
+// K4b' cluster attention for few frames in flight: the 50-row window of one (stream, frame, head) is
+// split over a thread-block CLUSTER of 8 CTAs (8 SMs); every CTA reduces its rows to an
+// un-normalised partial (max, sum, o[1552]) in its own shared memory, then the cluster merges the
+// partials through distributed shared memory (each CTA owns 1/8 of the output columns and reads
+// that slice from its 7 peers) and writes the final, normalised head output.  No scratch round trip
+// through L2/HBM, no separate merge pass.  grid (T, 4*8, B), cluster (1, 8, 1), 256 threads.
+constexpr int ATT_CL = 8;
+
+__global__ void __launch_bounds__(256)
+attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
+                    const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T) {
+    namespace cg = cooperative_groups;
+    __shared__ __align__(16) float qs[QK_LD];
+    __shared__ __align__(16) float os[V_DIM];     // this CTA's partial output
+    __shared__ float ml[2];                        // its running max and sum
+    __shared__ float sc[16];
+    __shared__ float coef[ATT_CL];
+    griddep_launch();
+    griddep_wait();
+    cg::cluster_group cluster = cg::this_cluster();
+    const int t = blockIdx.x, h = blockIdx.y / ATT_CL, rk = blockIdx.y % ATT_CL, b = blockIdx.z, tid = threadIdx.x;
+    const int base = ATT / ATT_CL, rem = ATT % ATT_CL;           // 6 rows each, the first 2 ranks take 7
+    const int j0 = rk * base + min(rk, rem), nr = base + (rk < rem ? 1 : 0);
+    const int64_t bh = (int64_t)b * NHEAD + h;
+    const float* kb;
+    const float* vb;
+    if (T == 1) {
+        const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+        kb = sb + BK_K + (int64_t)h * ATT * QK_LD;
+        vb = sb + BK_V + (int64_t)h * ATT * V_DIM;
+    } else {
+        kb = Kall + (bh * (ATT - 1 + T) + t) * QK_LD;
+        vb = Vall + (bh * (ATT - 1 + T) + t) * V_DIM;
+    }
+    kb += (int64_t)j0 * QK_LD;
+    vb += (int64_t)j0 * V_DIM;
+    const float* q = Qbuf + (bh * T + t) * QK_LD;
+    for (int i = tid; i < QK_LD / 4; i += 256)
+        reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(q)[i];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const float scale = rsqrtf((float)QK_DIM);
+    if (warp < nr) {                               // one warp per key row (nr <= 7)
+        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)warp * QK_LD);
+        float4 kv[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = lane + 32 * u;
+            kv[u] = (i < QK_LD / 4) ? kr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = lane + 32 * u;
+            if (i < QK_LD / 4) {
+                const float4 qv = reinterpret_cast<const float4*>(qs)[i];
+                s += kv[u].x * qv.x + kv[u].y * qv.y + kv[u].z * qv.z + kv[u].w * qv.w;
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) sc[warp] = s * scale;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float a0 = (lane < nr) ? sc[lane] : -INFINITY;
+        const float mx = warp_max(a0);
+        const float e0 = (lane < nr) ? __expf(a0 - mx) : 0.f;
+        const float lsum = warp_sum(e0);
+        if (lane < nr) sc[lane] = e0;
+        if (lane == 0) { ml[0] = mx; ml[1] = lsum; }
+    }
+    __syncthreads();
+    for (int c4 = tid; c4 < V_DIM / 4; c4 += 256) {
+        float4 v[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float p = (j < nr) ? sc[j] : 0.f;
+            acc.x = fmaf(p, v[j].x, acc.x); acc.y = fmaf(p, v[j].y, acc.y);
+            acc.z = fmaf(p, v[j].z, acc.z); acc.w = fmaf(p, v[j].w, acc.w);
+        }
+        reinterpret_cast<float4*>(os)[c4] = acc;
+    }
+    cluster.sync();                                // every CTA's partial is complete and visible cluster-wide
+    // ---- merge through distributed shared memory ---------------------------------------------------
+    if (tid < ATT_CL) {
+        const float* pml = cluster.map_shared_rank(ml, tid);
+        sc[8 + tid] = pml[0];                      // peer maxima
+        coef[tid] = pml[1];                        // peer sums (turned into weights below)
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float mstar = -INFINITY;
+        for (int p = 0; p < ATT_CL; ++p) mstar = fmaxf(mstar, sc[8 + p]);
+        float den = 0.f, wgt[ATT_CL];
+        for (int p = 0; p < ATT_CL; ++p) { wgt[p] = __expf(sc[8 + p] - mstar); den += wgt[p] * coef[p]; }
+        const float inv = 1.f / den;
+        for (int p = 0; p < ATT_CL; ++p) coef[p] = wgt[p] * inv;
+    }
+    __syncthreads();
+    constexpr int COLS = (V_DIM / 4 + ATT_CL - 1) / ATT_CL;      // 49 float4 columns per CTA
+    float* zr = Z + ((int64_t)b * T + t) * NF * CH;
+    if (tid < COLS) {
+        const int c4 = rk * COLS + tid;
+        if (c4 < V_DIM / 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < ATT_CL; ++p) {
+                const float4 v = reinterpret_cast<const float4*>(cluster.map_shared_rank(os, p))[c4];
+                const float cf = coef[p];
+                acc.x = fmaf(cf, v.x, acc.x); acc.y = fmaf(cf, v.y, acc.y);
+                acc.z = fmaf(cf, v.z, acc.z); acc.w = fmaf(cf, v.w, acc.w);
+            }
+            const int f = c4 >> 2, c0 = (c4 & 3) * 4;            // feature f*16 + c -> channel h*16 + c
+            *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
+        }
+    }
+    cluster.sync();                                // nobody leaves while a peer may still read its shared memory
+}
+
 // ------------------------------------------------------------------------------------------
 // K4c attention output: Linear(64->64) + PReLU + LayerNorm over (F, C) + residual
 // (tfgridnet_causal.py:583-588); for block 0 the speaker gate that the reference applies to the
@@ -522,18 +644,18 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     griddep_launch();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
-    if (tid == 0) {                 // parameters: before the dependency wait
-        mbar_expect_tx(&bars[0], (64 * 64 + 2 * FC) * 4);
-        tma_load_1d(Ws, w.wp_t, 64 * 64 * 4, &bars[0]);
-        tma_load_1d(Gs, w.lnp_g, FC * 4, &bars[0]);
-        tma_load_1d(Bs, w.lnp_b, FC * 4, &bars[0]);
-    }
+    // parameters: before the dependency wait
+    if (tid == 0) mbar_expect_tx(&bars[0], (64 * 64 + 2 * FC) * 4);
+    __syncthreads();
+    tma_load_split(Ws, w.wp_t, 64 * 64 * 4, &bars[0], tid, 256);
+    tma_load_split(Gs, w.lnp_g, FC * 4, &bars[0], tid, 256);
+    tma_load_split(Bs, w.lnp_b, FC * 4, &bars[0], tid, 256);
     griddep_wait();
-    if (tid == 0) {                 // chain data: the residual rows and (block 0) the gate
-        mbar_expect_tx(&bars[1], (apply_gate ? 2 : 1) * FC * 4);
-        tma_load_1d(Xr, xr, FC * 4, &bars[1]);
-        if (apply_gate) tma_load_1d(Gt, gate, FC * 4, &bars[1]);
-    }
+    // chain data: the residual rows and (block 0) the gate
+    if (tid == 0) mbar_expect_tx(&bars[1], (apply_gate ? 2 : 1) * FC * 4);
+    __syncthreads();
+    tma_load_split(Xr, xr, FC * 4, &bars[1], tid, 256);
+    if (apply_gate) tma_load_split(Gt, gate, FC * 4, &bars[1], tid, 256);
     if (nsplit == 1) {
         const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
         for (int i = tid; i < 100 * 16; i += 256) {
@@ -682,16 +804,16 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
     const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
     float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
-    if (tid == 0) {
-        fence_proxy_async();                // (zero-fill above went through the generic proxy)
+    {
         int nfr = 0;
         for (int slot = 0; slot < 4; ++slot) nfr += (t - 3 + slot >= -2) ? 1 : 0;
-        mbar_expect_tx(&bars[0], nfr * FC * 4);
+        if (tid == 0) { fence_proxy_async(); mbar_expect_tx(&bars[0], nfr * FC * 4); }
+        __syncthreads();
         for (int slot = 0; slot < 4; ++slot) {
             const int tt = t - 3 + slot;
             if (tt < -2) continue;
             const float* src = (tt >= 0) ? X + ((int64_t)b * T + tt) * FC : db + (2 + tt) * FC;
-            tma_load_1d(Xs + (slot * 99 + 1) * 64, src, FC * 4, &bars[0]);
+            tma_load_split(Xs + (slot * 99 + 1) * 64, src, FC * 4, &bars[0], tid, 256);
         }
     }
     mbar_wait(&bars[0], 0);
@@ -739,11 +861,10 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     // synthesis: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}; filters streamed in two halves
     float part[2] = {0.f, 0.f};             // this thread's outputs: item = tid and tid + 256 of (ear, n)
     for (int half = 0; half < 2; ++half) {
-        if (tid == 0) {
-            fence_proxy_async();            // the region was read/written through the generic proxy until now
-            mbar_expect_tx(&bars[1 + half], BACK_WS_HALF * NFFT * 4);
-            tma_load_1d(Xs, w.ws + (int64_t)half * BACK_WS_HALF * NFFT, BACK_WS_HALF * NFFT * 4, &bars[1 + half]);
-        }
+        fence_proxy_async();                // the region was read through the generic proxy until now
+        if (tid == 0) mbar_expect_tx(&bars[1 + half], BACK_WS_HALF * NFFT * 4);
+        __syncthreads();
+        tma_load_split(Xs, w.ws + (int64_t)half * BACK_WS_HALF * NFFT, BACK_WS_HALF * NFFT * 4, &bars[1 + half], tid, 256);
         mbar_wait(&bars[1 + half], 0);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
