@@ -302,12 +302,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS);
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
-    CK(launch_k(false, front_kernel, dim3(T, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T, a.pos_rel));
+    CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
+                a.pos_rel, emb, PRE));
     MARK("front");
-    CK(launch_k(pdl, spk_gemv_kernel, dim3(FC / 32, B), dim3(256), 0, st, emb, PRE, (const float*)state, ss, e->w));
-    MARK("spk_gemv");
-    CK(launch_k(pdl, spk_ln_kernel, dim3(B), dim3(256), 0, st, emb, (const float*)PRE, state, ss, e->w));
-    MARK("spk_ln");
     if (int rc = do_tap()) return rc;
 
     for (int b = 0; b < e->n_blocks; ++b) {
@@ -538,7 +535,7 @@ int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* off, 
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !n) return fail(1, "bad argument");
-    *n = 3 + e->n_blocks * (frames == 1 && e->use_mid ? 6 : 9 + (frames > 1 ? 1 : 0)) + 1;
+    *n = 1 + e->n_blocks * (frames == 1 && e->use_mid ? 6 : 9 + (frames > 1 ? 1 : 0)) + 1;
     return 0;
 }
 

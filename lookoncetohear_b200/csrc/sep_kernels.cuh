@@ -73,16 +73,24 @@ __global__ void set_clip_base_kernel(float* state) {
 // look-ahead zeros of net.py:8-18,56-58).  Frames before the call start come from conv_buf.
 constexpr size_t FRONT_SMEM = (size_t)NFFT * 196 * sizeof(float);     // analysis filters, staged by TMA
 
+__device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ pre, float* __restrict__ state,
+                             int64_t sstride, const SepWeights& w, int b, float* red);
+
 __global__ void __launch_bounds__(256)
 front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
              float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T,
-             int pos_rel) {
+             int pos_rel, const float* __restrict__ emb, float* __restrict__ spk_pre) {
     extern __shared__ __align__(16) float wat_s[];     // [192][196]
-    __shared__ float xs[NMIC][448];
+    __shared__ __align__(16) float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
     __shared__ __align__(8) unsigned long long wbar;
     griddep_launch();
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (t == T) {                      // the extra CTA of this stream: speaker-gate memo
+        griddep_wait();
+        spk_gate_cta(emb, spk_pre, state, sstride, w, b, &xs[0][0]);
+        return;
+    }
     if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
     __syncthreads();
     if (tid == 0) mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM);
@@ -164,48 +172,42 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K6 speaker gate: g = LN_6208(W e + b), stored (f, c)   (tfgridnet_causal.py:247-248)
-// Memoised on the device: if the embedding equals the one the cached gate was built from, both
-// kernels return immediately (the reference recomputes it every call; results are identical).
-__global__ void __launch_bounds__(256)
-spk_gemv_kernel(const float* __restrict__ emb, float* __restrict__ pre, const float* __restrict__ state,
-                int64_t sstride, SepWeights w) {
-    __shared__ __align__(16) float es[SPK];
-    griddep_launch();
-    griddep_wait();
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+// K6 speaker gate: g = LN_6208(W e + b), stored (f, c)   (tfgridnet_causal.py:247-248).
+// The reference recomputes it on every call; it only changes when the embedding does, so it is
+// memoised ON THE DEVICE: one extra CTA per stream rides along with front_kernel, compares the
+// embedding with the one the cached gate was built from and returns at once if they are equal
+// (the streaming steady state).  Otherwise that CTA rebuilds the gate (6208x256 GEMV + LayerNorm).
+__device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ pre, float* __restrict__ state,
+                             int64_t sstride, const SepWeights& w, int b, float* red /* >= 288 floats smem */) {
+    const int tid = threadIdx.x;
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float e = emb[(int64_t)b * SPK + tid];
     const int same = __syncthreads_and(e == st[ST_EMB + tid]);
     if (same) return;
+    float* es = red + 32;                      // [256] embedding
     es[tid] = e;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     const float4 e0 = *reinterpret_cast<const float4*>(es + lane * 4);
     const float4 e1 = *reinterpret_cast<const float4*>(es + 128 + lane * 4);
-    for (int r = 0; r < 4; ++r) {
-        const int n = blockIdx.x * 32 + warp * 4 + r;
-        const float4* wr = reinterpret_cast<const float4*>(w.we + (int64_t)n * SPK);
-        const float4 a0 = __ldg(wr + lane), a1 = __ldg(wr + 32 + lane);
-        float s = a0.x * e0.x + a0.y * e0.y + a0.z * e0.z + a0.w * e0.w +
-                  a1.x * e1.x + a1.y * e1.y + a1.z * e1.z + a1.w * e1.w;
-        s = warp_sum(s);
-        if (lane == 0) pre[(int64_t)b * FC + n] = s + __ldg(w.be + n);
+    float* p = pre + (int64_t)b * FC;
+    for (int n0 = warp * 4; n0 < FC; n0 += 32) {          // 4 rows per warp per pass: 8 loads in flight per lane
+        float4 a0[4], a1[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float4* wr = reinterpret_cast<const float4*>(w.we + (int64_t)(n0 + r) * SPK);
+            a0[r] = __ldg(wr + lane);
+            a1[r] = __ldg(wr + 32 + lane);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float s = a0[r].x * e0.x + a0[r].y * e0.y + a0[r].z * e0.z + a0[r].w * e0.w +
+                      a1[r].x * e1.x + a1[r].y * e1.y + a1[r].z * e1.z + a1[r].w * e1.w;
+            s = warp_sum(s);
+            if (lane == 0) p[n0 + r] = s + __ldg(w.be + n0 + r);
+        }
     }
-}
-
-__global__ void __launch_bounds__(256)
-spk_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pre, float* __restrict__ state,
-              int64_t sstride, SepWeights w) {
-    __shared__ float red[32];
-    griddep_launch();
-    griddep_wait();
-    const int b = blockIdx.x, tid = threadIdx.x;
-    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
-    const float e = emb[(int64_t)b * SPK + tid];
-    const int same = __syncthreads_and(e == st[ST_EMB + tid]);
-    if (same) return;
-    const float* p = pre + (int64_t)b * FC;
+    __syncthreads();
     float s = 0.f;
     for (int i = tid; i < FC; i += 256) s += p[i];
     const float mu = block_sum(s, red) * (1.f / FC);
