@@ -295,6 +295,17 @@ def main():
             torch.cuda.synchronize()
             lat.append(time.perf_counter() - t0)
         extras["chunk_latency_us"] = 1e6 * statistics.median(lat)
+        # the same 500-hop stream with the hops run strictly one after the other (no wavefront pipelining)
+        net.set_option("pipeline", 0)
+        for it in range(3):
+            st = net.init_buffers(1, dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            net.stream_dev(x_dev, emb, chunks_per_call=1, state=st, n_calls=FRAMES, out=y_dev)
+            b.record()
+            torch.cuda.synchronize()
+            extras["frames_per_s_unpipelined"] = FRAMES / (a.elapsed_time(b) * 1e-3)
+        net.set_option("pipeline", 1)
         # buffered throughput: more hops per call (latency traded for throughput), same clip, same state API
         buf = {}
         for c in (4, 20, 500):
@@ -308,6 +319,36 @@ def main():
                 torch.cuda.synchronize()
                 buf[str(c)] = FRAMES / (a.elapsed_time(b) * 1e-3)
         extras["frames_per_s_by_chunks_per_call"] = buf
+        # BASELINE configs[4] per-GPU shape: 256 independent streams advancing one hop per step.  This is
+        # the regime the HBM roofline of SURVEY.md 8(d) describes (5.5 MB of state per hop per stream).
+        try:
+            nb, nsteps = 256, 60
+            xb, _ = synth.mixture(nb, HOP * nsteps, seed0=5000)
+            xb = xb.to(dev)
+            eb = synth.embedding(nb, seed0=6000)[:, 0].to(dev)
+            yb = torch.empty(nb, 2, HOP * nsteps, device=dev)
+            best = None
+            for it in range(3):
+                stb = net.init_buffers(nb, dev)
+                net.stream_dev(xb, eb, chunks_per_call=1, state=stb, n_calls=10, out=yb)     # warm (gate build, graph)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                net.stream_dev(xb[..., HOP * 10:], eb, chunks_per_call=1, state=stb, n_calls=nsteps - 10,
+                               out=yb[..., HOP * 10:])
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b)
+                best = ms if best is None else min(best, ms)
+            fps = nb * (nsteps - 10) / (best * 1e-3)
+            pkb = peaks()
+            extras["batched_streaming_256"] = {
+                "streams": nb, "frames_per_s": fps, "rtf_aggregate": fps / 125.0, "ms_per_hop_step": best / (nsteps - 10),
+                "hbm_gbs_algorithmic": fps * BYTES_PER_FRAME / 1e9,
+                "hbm_frac": fps * BYTES_PER_FRAME / 1e9 / pkb["hbm_gbs"], "peak_source": pkb["source"],
+                "note": "state (1.38 GB) >> L2: every hop re-reads each stream's K/V rings from HBM"}
+            del xb, yb, stb
+        except Exception as exc:                                   # never let an extra break the bench line
+            extras["batched_streaming_256"] = {"error": repr(exc)[:200]}
     if rank == 0:
         # per-kernel device times of one streaming chain (CUDA events on the launching stream)
         prof = profile_chain(net, x_dev, emb, dev, cpc)
@@ -341,7 +382,11 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": value / world / 125.0,
             "config": {"workload": "streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); "
                                    "4 s clip = 500 hops per step, fresh state per step",
-                       "chunks_per_call": cpc, "parallelism": f"dp{world} (independent streams, weights broadcast over NCCL)",
+                       "chunks_per_call": cpc,
+                       "pipeline": "wavefront over (block, hop): up to %d one-hop chains per CUDA graph on 8 streams; every hop "
+                                   "is its own T=1 chain with the state carried (frames_per_s_unpipelined / chunk_latency_us "
+                                   "give the strictly sequential figures)" % net.pipeline_frames(),
+                       "parallelism": f"dp{world} (independent streams, weights broadcast over NCCL)",
                        "l2": "flushed (256 MiB write) between timed iterations"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_calls * 2 * (HOP * cpc + 64) * 4,
                     "d2h_bytes_per_step": n_calls * 2 * HOP * cpc * 4, "rtf": e2e_value / world / 125.0,

@@ -96,10 +96,14 @@ int l2h_sep_forward(void* handle, const float* x_dev, int64_t x_batch_stride, in
                     int32_t frames, void* workspace_dev, size_t workspace_bytes, uint32_t flags,
                     void* stream);
 
-/* Streaming with HOST buffers (the end-to-end path): for i in [0, n_chunks):
- *   H2D x_host[:, :, 128*i*chunks_per_call : ... + 128*chunks_per_call + 64]  (pinned memory),
- *   forward of chunks_per_call frames, D2H of the 128*chunks_per_call new samples; then one
- *   stream synchronise at the end.  x_host [batch][num_ch][x_len], y_host [batch][num_src][y_len]. */
+/* Streaming with HOST buffers (the end-to-end path).  Per round: H2D of the round's samples (+64
+ * look-ahead) from pinned memory, the kernel chains, D2H of the new samples; one stream synchronise at
+ * the end.  A round is one call of chunks_per_call hops -- or, for chunks_per_call == 1 with pipelining
+ * enabled, a group of up to l2h_sep_pipeline_frames() one-hop calls that run as one wavefront-pipelined
+ * graph (every hop is still its own T=1 chain with the state carried hop to hop).
+ * x_host [batch][num_ch][x_len], y_host [batch][num_src][y_len]; x_stage_dev / y_stage_dev must hold
+ * [batch][ch][128*G + 64] / [batch][src][128*G] floats with G = max(chunks_per_call, pipeline frames);
+ * workspace from l2h_sep_stream_workspace_bytes(). */
 int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const float* emb_dev,
                         void* state_dev, float* y_host, int32_t y_len, int32_t batch,
                         int32_t n_calls, int32_t chunks_per_call, float* x_stage_dev,
@@ -108,11 +112,21 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
 
 /* Streaming with DEVICE buffers: x_dev [batch][num_ch][x_len] holds whole clips, y_dev
  * [batch][num_src][y_len]; n_calls chained calls of chunks_per_call frames each, starting at the
- * beginning of x_dev and continuing the state.  Each call is one CUDA-graph replay; the chunk a
- * replay works on is derived on the device from the state's frame counter.  Asynchronous. */
+ * beginning of x_dev and continuing the state.  Calls are CUDA-graph replays; the chunk a replay
+ * works on is derived on the device from the state's frame counter.  With chunks_per_call == 1 the
+ * one-hop chains of up to l2h_sep_pipeline_frames() consecutive hops are captured as ONE graph on 8
+ * streams with (block, frame) wavefront dependencies, so different blocks work on different hops
+ * concurrently (set L2H_PIPE=0 to run the hops strictly one after the other).  Asynchronous. */
 int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const float* emb_dev,
                        void* state_dev, float* y_dev, int32_t y_len, int32_t batch, int32_t n_calls,
                        int32_t chunks_per_call, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* workspace for the two streaming entry points (one slot per in-flight hop when pipelining) and the
+ * number of one-hop calls a pipelined graph holds (1 = pipelining off) */
+int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_per_call, size_t* bytes);
+int l2h_sep_pipeline_frames(void* handle, int32_t* frames);
+/* runtime switches (also env L2H_PIPE / L2H_PDL / L2H_MID at create): "pipeline", "pdl", "fused_mid" = 0 | 1 */
+int l2h_sep_set_option(void* handle, const char* name, int32_t value);
 
 /* where the tap area starts inside the workspace (floats) and its stage count; stage s holds
  * [batch*frames*97*64] floats: 0 = encoder out, then per block: after intra, after inter, block out */

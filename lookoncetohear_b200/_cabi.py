@@ -61,6 +61,10 @@ _SIGS = {
                                       ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.c_void_p]),
+    "l2h_sep_stream_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                     ctypes.POINTER(ctypes.c_size_t)]),
+    "l2h_sep_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32]),
+    "l2h_sep_pipeline_frames": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     "l2h_sep_tap_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]),
     "l2h_sep_launches_per_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,

@@ -80,16 +80,13 @@ L2H_DEVINL void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// A single large bulk copy is served slowly (measured: 150 KB by one instruction ~ 10 us on one SM); many
-// 2 KB copies issued by different threads keep enough requests in flight to run at L2 speed.
-// Called by ALL threads of the CTA (each issues its share); the caller arms the barrier with the byte total.
+// Stage a contiguous block with ONE bulk copy issued by thread 0.  Measured on B200 for a single CTA
+// and an L2-resident source (profiles/r01c_copy_microbench.txt): 150 KB in 0.88 us (170 GB/s) with one
+// cp.async.bulk, vs 1.26 us as 74 x 2 KB bulk copies and 2.35 us as an LDG.128 -> STS.128 loop.
+// Called by all threads (uniform call sites); the caller arms the barrier with the byte total.
 L2H_DEVINL void tma_load_split(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar,
-                               int tid, int nthreads) {
-    constexpr unsigned CH = 2048;
-    for (unsigned off = (unsigned)tid * CH; off < bytes; off += (unsigned)nthreads * CH) {
-        const unsigned n = (bytes - off < CH) ? (bytes - off) : CH;
-        tma_load_1d(reinterpret_cast<char*>(dst_smem) + off, reinterpret_cast<const char*>(src_gmem) + off, n, bar);
-    }
+                               int tid, int /*nthreads*/) {
+    if (tid == 0) tma_load_1d(dst_smem, src_gmem, bytes, bar);
 }
 // order earlier generic-proxy accesses of shared memory before later async-proxy (TMA) writes to it
 L2H_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -57,6 +57,9 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t pipe_streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> pipe_events;
+    bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
 };
@@ -303,7 +306,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
     CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
-                a.pos_rel, emb, PRE));
+                a.pos_rel, emb, PRE, 0));
     MARK("front");
     if (int rc = do_tap()) return rc;
 
@@ -361,7 +364,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             MARK("kv_gather");
         }
         CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
-                    (const float*)(fused_mid ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T));
+                    (const float*)(fused_mid ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
         MARK("qkv");
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
@@ -377,9 +380,132 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (int rc = do_tap()) return rc;
     }
     CK(launch_k(pdl, back_kernel, dim3(T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
-                a.pos_rel));
+                a.pos_rel, 0, 1));
     MARK("back");
 #undef MARK
+    return 0;
+}
+
+// ---- wavefront pipeline over (block, frame) for one-frame calls ---------------------------------------
+// Work item (block b, frame t) depends only on (b-1, t) and (b, t-1); moreover the intra
+// half of a block (W_ih GEMM + 97-step BiLSTM, "stage A") needs nothing from frame t-1 at all.  A graph
+// of K consecutive one-frame chains is therefore captured on 8 streams -- front | A0 B0 | A1 B1 | A2 B2 |
+// back -- with event edges (b-1,t) -> (b,t); consecutive frames flow through the stages like a
+// systolic wavefront and the steady-state cost per hop is the slowest stage (the BiLSTM recurrence)
+// instead of the whole chain.  Every frame owns a workspace slot; state addressing uses
+// pos + frame_k / parity(ncalls + frame_k); the header advances once, at the last frame.
+constexpr int PIPE_MAX_FRAMES = 100;
+
+static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
+
+static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t origin) {
+    if (e->n_blocks != 3) return fail(1, "pipeline graph is specialised to 3 blocks");
+    const int B = a.B;
+    const Workspace ws = carve(e->n_blocks, B, 1, 0);
+    const int64_t slot = ws.total;
+    if ((size_t)slot * K * sizeof(float) > a.ws_bytes) return fail(1, "workspace too small for the pipelined stream");
+    const int64_t ss = stream_stride(e->n_blocks);
+    const int rows = B * NF;
+    const int nsplit = attn_splits(B, 1);
+    float* state = a.state;
+    for (auto& ps : e->pipe_streams)
+        if (!ps) CK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    size_t ev_used = 0;
+    auto next_event = [&](cudaEvent_t* out) -> int {
+        if (ev_used == e->pipe_events.size()) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->pipe_events.push_back(ev);
+        }
+        *out = e->pipe_events[ev_used++];
+        return 0;
+    };
+    auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {     // `to` continues after everything enqueued on `from`
+        cudaEvent_t ev;
+        if (int rc = next_event(&ev)) return rc;
+        CK(cudaEventRecord(ev, from));
+        CK(cudaStreamWaitEvent(to, ev, 0));
+        return 0;
+    };
+    cudaStream_t sF = origin, sBack = e->pipe_streams[7];
+    cudaStream_t sA[3] = {e->pipe_streams[1], e->pipe_streams[3], e->pipe_streams[5]};
+    cudaStream_t sB[3] = {e->pipe_streams[2], e->pipe_streams[4], e->pipe_streams[6]};
+    // fork: bring the worker streams into the capture
+    for (int i = 1; i < 8; ++i)
+        if (int rc = edge(origin, e->pipe_streams[i])) return rc;
+    for (int k = 0; k < K; ++k) {
+        float* wsp = a.wsp + (int64_t)k * slot;
+        float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
+        float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW; float* PRE = a.wsp + ws.PRE;   // PRE: front stream only
+        // x / y: either clip-relative addressing on the device (pos_rel) or a host-computed chunk offset
+        const float* xk = a.pos_rel ? a.x : a.x + (int64_t)k * HOP;
+        const int xlen_k = a.pos_rel ? a.x_len : std::max(0, std::min(a.x_len - k * HOP, HOP + LOOKAHEAD));
+        float* yk = a.pos_rel ? a.y : a.y + (int64_t)k * HOP;
+        const int ylen_k = a.pos_rel ? a.y_len : std::max(0, std::min(a.y_len - k * HOP, HOP));
+        CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, xk, a.xbs, a.xcs, xlen_k, X, state, ss, e->w, 1,
+                    a.pos_rel, a.emb, PRE, k));
+        if (int rc = edge(sF, sA[0])) return rc;
+        for (int b = 0; b < 3; ++b) {
+            const BlockWeights& W = e->bw[b];
+            GemmArgs g{};
+            g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
+            g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
+            CK(launch_rows_gemm(g, sA[b], false));
+            LstmArgs l{};
+            l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
+            l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
+            CK(launch_lstm_rec(l, sA[b], false));
+            if (int rc = edge(sA[b], sB[b])) return rc;
+            CK(launch_k(false, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, sB[b], (const float*)Y, X,
+                        QKVRAW, state, ss, b, W));
+            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sB[b], (const float*)X, (const float*)QKVRAW,
+                        Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
+            if (nsplit > 1) {
+                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sB[b],
+                                  (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1));
+            } else {
+                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sB[b], (const float*)Q, (const float*)nullptr,
+                            (const float*)nullptr, (const float*)state, ss, b, Z, (float*)nullptr, 1, 1));
+            }
+            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sB[b], (const float*)Z, X, (const float*)state, ss,
+                        W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
+            if (int rc = edge(sB[b], b < 2 ? sA[b + 1] : sBack)) return rc;
+        }
+        CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, yk, a.ybs, a.ycs, ylen_k, state, ss,
+                    e->w, 1, a.pos_rel, k, K));
+    }
+    // join
+    for (int i = 1; i < 8; ++i)
+        if (int rc = edge(e->pipe_streams[i], origin)) return rc;
+    return 0;
+}
+
+// K chained one-frame calls as one pipelined graph (cached on the argument set + K)
+static int run_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t st) {
+    std::vector<int64_t> key = {(int64_t)a.x, a.xbs, a.xcs, a.x_len, (int64_t)a.emb, (int64_t)a.state, (int64_t)a.y,
+                                a.ybs, a.ycs, a.y_len, a.B, -K, (int64_t)a.wsp, (int64_t)a.flags, a.pos_rel};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        if (!e->committed) return fail(4, "weights not committed");
+        if (int rc = set_attrs()) return rc;
+        if (!e->pipe_streams[0]) CK(cudaStreamCreateWithFlags(&e->pipe_streams[0], cudaStreamNonBlocking));
+        if (e->graphs.size() >= 32) {
+            for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+            e->graphs.clear();
+        }
+        cudaStream_t origin = e->pipe_streams[0];
+        CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_pipeline(e, a, K, origin);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(origin, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(3, std::string("cudaStreamEndCapture (pipeline): ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = e->graphs.emplace(key, exec).first;
+    }
+    CK(cudaGraphLaunch(it->second, st));
     return 0;
 }
 
@@ -434,6 +560,7 @@ int l2h_sep_create(const l2h_sep_config* c, void** handle) {
     e->n_blocks = c->B;
     if (const char* v = getenv("L2H_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("L2H_MID")) e->use_mid = atoi(v) != 0;
+    if (const char* v = getenv("L2H_PIPE")) e->use_pipe = atoi(v) != 0;
     build_layout(e);
     *handle = e;
     return 0;
@@ -444,6 +571,8 @@ int l2h_sep_destroy(void* handle) {
     if (!e) return 0;
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (auto& ps : e->pipe_streams) if (ps) cudaStreamDestroy(ps);
+    for (auto& ev : e->pipe_events) cudaEventDestroy(ev);
     if (e->dev) cudaFree(e->dev);
     delete e;
     return 0;
@@ -555,21 +684,30 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !x_host || !emb || !state || !y_host || !x_stage || !y_stage || !ws) return fail(1, "null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int in_len = HOP * cpc + LOOKAHEAD, out_len = HOP * cpc;
-    for (int i = 0; i < n_calls; ++i) {
-        const int s0 = i * out_len;
-        int n_in = x_len - s0;
-        if (n_in > in_len) n_in = in_len;
+    // hops moved per host<->device round: one call's worth, or (one-hop calls, pipelining on) a group of up to
+    // PIPE_MAX_FRAMES hops that then run as ONE wavefront-pipelined graph of one-hop chains
+    const bool pipe = cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1;
+    int group = cpc;
+    if (pipe) {
+        const int64_t slot = pipe_slot_floats(e, batch);
+        group = (int)std::min<int64_t>(std::min(PIPE_MAX_FRAMES, n_calls), (int64_t)(ws_bytes / sizeof(float)) / slot);
+        if (group < 2) group = 1;
+    }
+    const int hops_total = n_calls * cpc;
+    const int in_len = HOP * group + LOOKAHEAD, out_len = HOP * group;      // staging strides
+    for (int h0 = 0; h0 < hops_total; h0 += group) {
+        const int hops = std::min(group, hops_total - h0);
+        const int s0 = h0 * HOP;
+        int n_in = std::min(x_len - s0, HOP * hops + LOOKAHEAD);
         if (n_in <= 0) return fail(1, "x_host shorter than n_calls * chunks_per_call * 128 samples");
         CK(cudaMemcpy2DAsync(x_stage, in_len * sizeof(float), x_host + s0, (size_t)x_len * sizeof(float),
                              (size_t)n_in * sizeof(float), (size_t)batch * NMIC, cudaMemcpyHostToDevice, st));
-        // (a short last chunk changes x_len and therefore the graph key: at most two graphs)
+        // (a short last round changes the sizes and therefore the graph key: at most two graphs)
         ChainArgs a{x_stage, (int64_t)NMIC * in_len, in_len, n_in, emb, static_cast<float*>(state), y_stage,
-                    (int64_t)NSRC * out_len, out_len, out_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 0};
-        int rc = run_chain(e, a, st, true);
+                    (int64_t)NSRC * out_len, out_len, HOP * hops, batch, pipe ? 1 : hops, static_cast<float*>(ws), ws_bytes, 0, 0};
+        int rc = (pipe && hops > 1) ? run_pipeline(e, a, hops, st) : run_chain(e, a, st, true);
         if (rc) return rc;
-        int n_out = y_len - s0;
-        if (n_out > out_len) n_out = out_len;
+        const int n_out = std::min(y_len - s0, HOP * hops);
         if (n_out > 0)
             CK(cudaMemcpy2DAsync(y_host + s0, (size_t)y_len * sizeof(float), y_stage, out_len * sizeof(float),
                                  (size_t)n_out * sizeof(float), (size_t)batch * NSRC, cudaMemcpyDeviceToHost, st));
@@ -589,8 +727,53 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
     CK(cudaGetLastError());
     ChainArgs a{x_dev, (int64_t)NMIC * x_len, x_len, x_len, emb, static_cast<float*>(state), y_dev,
                 (int64_t)NSRC * y_len, y_len, y_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 1};
+    if (cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1) {
+        // groups of up to PIPE_MAX_FRAMES one-frame calls, each group one wavefront-pipelined graph
+        const int64_t slot = pipe_slot_floats(e, batch);
+        int kmax = (int)std::min<int64_t>(PIPE_MAX_FRAMES, (int64_t)(ws_bytes / sizeof(float)) / slot);
+        if (kmax >= 2) {
+            int done = 0;
+            while (done < n_calls) {
+                const int K = std::min(kmax, n_calls - done);
+                if (K == 1) { if (int rc = run_chain(e, a, st, true)) return rc; }
+                else if (int rc = run_pipeline(e, a, K, st)) return rc;
+                done += K;
+            }
+            return 0;
+        }
+    }
     for (int i = 0; i < n_calls; ++i)
         if (int rc = run_chain(e, a, st, true)) return rc;
+    return 0;
+}
+
+int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_per_call, size_t* bytes) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !bytes || batch <= 0 || chunks_per_call <= 0) return fail(1, "bad argument");
+    if (chunks_per_call == 1 && e->use_pipe)
+        *bytes = (size_t)pipe_slot_floats(e, batch) * PIPE_MAX_FRAMES * sizeof(float);
+    else
+        *bytes = (size_t)carve(e->n_blocks, batch, chunks_per_call, 0).total * sizeof(float);
+    return 0;
+}
+
+int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !name) return fail(1, "bad argument");
+    const std::string n(name);
+    if (n == "pipeline") e->use_pipe = value != 0;
+    else if (n == "pdl") e->use_pdl = value != 0;
+    else if (n == "fused_mid") e->use_mid = value != 0;
+    else return fail(2, "unknown option: " + n);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting
+    e->graphs.clear();
+    return 0;
+}
+
+int l2h_sep_pipeline_frames(void* handle, int32_t* frames) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !frames) return fail(1, "bad argument");
+    *frames = (e->use_pipe && e->use_mid && e->n_blocks == 3) ? PIPE_MAX_FRAMES : 1;
     return 0;
 }
 

@@ -79,7 +79,7 @@ __device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
              float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T,
-             int pos_rel, const float* __restrict__ emb, float* __restrict__ spk_pre) {
+             int pos_rel, const float* __restrict__ emb, float* __restrict__ spk_pre, int frame_k) {
     extern __shared__ __align__(16) float wat_s[];     // [192][196]
     __shared__ __align__(16) float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
@@ -97,15 +97,17 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     __syncthreads();
     tma_load_split(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar, tid, 256);     // 74 bulk copies in flight
     griddep_wait();
+    // frame_k: index of this one-frame call inside a pipelined multi-frame graph (0 otherwise); the
+    // header is advanced once, by the last frame of the graph
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
-    const int par = (int)(hdr->ncalls & 1);
+    const int par = (int)((hdr->ncalls + frame_k) & 1);
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* cb = st + ST_CONV + par * (2 * 4 * NF);
     float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
 
     for (int i = tid; i < 3 * 4 * 100; i += 256) (&U[0][0][0])[i] = 0.f;
     // pos_rel: x is a whole clip and this call starts at frame (pos - clip_base) of it
-    const int s0 = HOP * (t - 2) + (pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0);
+    const int s0 = HOP * (t - 2) + (pos_rel ? (int)(hdr->pos - hdr->clip_base + frame_k) * HOP : 0);
     for (int i = tid; i < NMIC * 448; i += 256) {
         const int m = i / 448, n = i % 448, s = s0 + n;
         xs[m][n] = (s >= 0 && s < x_len) ? x[(int64_t)b * x_bstride + (int64_t)m * x_cstride + s] : 0.f;
@@ -255,7 +257,7 @@ constexpr size_t QKV_SMEM = (size_t)(64 * 100 + 64 * NQKV + NF * QKV_PLD + QKV_L
 __global__ void __launch_bounds__(QKV_THREADS)
 qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __restrict__ Qbuf,
            float* __restrict__ Kall, float* __restrict__ Vall, float* __restrict__ state, int64_t sstride, int blk,
-           BlockWeights w, int T) {
+           BlockWeights w, int T, int frame_k) {
     extern __shared__ __align__(16) float sm[];
     float* Xt = sm;                      // [64][100]  k-major, rows padded to 100 (zeros)
     float* Ws = Xt + 64 * 100;           // [64][112]
@@ -360,7 +362,7 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
     const float* gam = LNP + (which == 0 ? 0 : (which == 1 ? 2 * QK_LD : 4 * QK_LD));
     const float* bet = LNP + (which == 0 ? QK_LD : (which == 1 ? 3 * QK_LD : 4 * QK_LD + V_DIM));
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
-    const long long pos = hdr->pos;
+    const long long pos = hdr->pos + frame_k;
     const int ld = (which == 2) ? V_DIM : QK_LD;
     float* dst0 = nullptr;   // linear scratch / Q buffer
     float* dst1 = nullptr;   // ring slot
@@ -773,7 +775,8 @@ static_assert(BACK_WS_HALF * NFFT <= 4 * 99 * 64, "filter half must fit in the f
 
 __global__ void __launch_bounds__(256)
 back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
-            int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel) {
+            int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int frame_k,
+            int frames_total) {
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]; later: filter halves
     float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
@@ -799,8 +802,8 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     __syncthreads();
     griddep_wait();
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
-    const int par = (int)(hdr->ncalls & 1);
-    const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
+    const int par = (int)((hdr->ncalls + frame_k) & 1);
+    const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base + frame_k) * HOP : 0;
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* db = st + ST_DECONV + par * (2 * FC);
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
@@ -904,8 +907,10 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
         __threadfence();
         const int prev = atomicAdd(&hdr->done, 1);
         if (prev == (int)(gridDim.x * gridDim.y) - 1) {
-            hdr->pos += T;
-            hdr->ncalls += 1;
+            if (frame_k == frames_total - 1) {      // the last frame of a (possibly pipelined) group advances the header
+                hdr->pos += (long long)T * frames_total;
+                hdr->ncalls += frames_total;
+            }
             hdr->done = 0;
             __threadfence();
         }

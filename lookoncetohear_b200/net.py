@@ -228,6 +228,22 @@ class Net(nn.Module):
             self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
         return self._ws, n.value
 
+    def _stream_workspace(self, device, batch, chunks_per_call):
+        n = ctypes.c_size_t()
+        _cabi.check(_cabi.lib().l2h_sep_stream_workspace_bytes(self._engine(), batch, chunks_per_call, ctypes.byref(n)))
+        if self._ws is None or self._ws.numel() < n.value or self._ws.device != device:
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+        return self._ws, n.value
+
+    def set_option(self, name, value):
+        """Engine switches: "pipeline" (wavefront pipelining of one-hop calls), "pdl", "fused_mid"."""
+        _cabi.check(_cabi.lib().l2h_sep_set_option(self._engine(), name.encode(), int(value)))
+
+    def pipeline_frames(self):
+        k = ctypes.c_int32()
+        _cabi.check(_cabi.lib().l2h_sep_pipeline_frames(self._engine(), ctypes.byref(k)))
+        return k.value
+
     @staticmethod
     def _require_cuda(t):
         if not t.is_cuda:
@@ -324,7 +340,7 @@ class Net(nn.Module):
         if state is None:
             state = self.init_buffers(Bsz, dev)
         y = out if out is not None else torch.empty(Bsz, self.num_src, n, dtype=torch.float32, device=dev)
-        ws, _ = self._workspace(dev, Bsz, chunks_per_call)
+        ws, _ = self._stream_workspace(dev, Bsz, chunks_per_call)
         emb = embed_dev.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().l2h_sep_stream_dev(
@@ -350,9 +366,10 @@ class Net(nn.Module):
         yh = torch.empty(Bsz, self.num_src, n_calls * step, dtype=torch.float32).pin_memory()
         if state is None:
             state = self.init_buffers(Bsz, dev)
-        xs = torch.empty(Bsz, self.num_ch, step + la, dtype=torch.float32, device=dev)
-        ys = torch.empty(Bsz, self.num_src, step, dtype=torch.float32, device=dev)
-        ws, _ = self._workspace(dev, Bsz, chunks_per_call)
+        grp = max(chunks_per_call, self.pipeline_frames() if chunks_per_call == 1 else 1)
+        xs = torch.empty(Bsz, self.num_ch, hop * grp + la, dtype=torch.float32, device=dev)
+        ys = torch.empty(Bsz, self.num_src, hop * grp, dtype=torch.float32, device=dev)
+        ws, _ = self._stream_workspace(dev, Bsz, chunks_per_call)
         emb = embed_dev.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().l2h_sep_stream_host(
