@@ -57,7 +57,7 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
-    cudaStream_t pipe_streams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t pipe_streams[32] = {};
     std::vector<cudaEvent_t> pipe_events;
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
@@ -369,6 +369,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
                               (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T));
+        } else if (T >= 2 * ATT_TQ) {                // many frames: query-tiled, one pass over 57 rows serves 8 queries
+            CK(launch_k(pdl, attn_tile_kernel, dim3((T + ATT_TQ - 1) / ATT_TQ, NHEAD, B), dim3(256), 0, st, (const float*)Q,
+                        (const float*)KALL, (const float*)VALL, Z, T));
         } else {
             CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
                         (const float*)VALL, (const float*)state, ss, b, Z, PART, 1, T));
@@ -387,14 +390,21 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 }
 
 // ---- wavefront pipeline over (block, frame) for one-frame calls ---------------------------------------
-// Work item (block b, frame t) depends only on (b-1, t) and (b, t-1); moreover the intra
-// half of a block (W_ih GEMM + 97-step BiLSTM, "stage A") needs nothing from frame t-1 at all.  A graph
-// of K consecutive one-frame chains is therefore captured on 8 streams -- front | A0 B0 | A1 B1 | A2 B2 |
-// back -- with event edges (b-1,t) -> (b,t); consecutive frames flow through the stages like a
-// systolic wavefront and the steady-state cost per hop is the slowest stage (the BiLSTM recurrence)
-// instead of the whole chain.  Every frame owns a workspace slot; state addressing uses
-// pos + frame_k / parity(ncalls + frame_k); the header advances once, at the last frame.
+// Work item (block b, hop t) depends only on (b-1, t) and (b, t-1), and inside a block
+// only part of the work carries state from hop to hop:
+//   A   = W_ih GEMM + 97-step BiLSTM        needs X_t only            -> PIPE_LANES hops of it run side by side
+//   B1  = mid_kernel (inter-LSTM step ...)   carries (h, c)            -> serial per block
+//   B2a = qkv + attention                    carries the K/V rings     -> serial per block
+//   B2b = attn_out                           needs Z_t, X_t only
+// A graph of K consecutive one-hop chains is captured on 1 + 3*(PIPE_LANES+3) + 1 streams with event edges
+// for exactly these dependencies; hops flow through the stages like a systolic wavefront and the
+// steady-state cost per hop is the slowest SERIAL stage instead of the whole 250 us chain.  Every hop owns a
+// workspace slot; state addressing uses pos + frame_k / parity(ncalls + frame_k); the header advances once,
+// at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
+// bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
 constexpr int PIPE_MAX_FRAMES = 100;
+constexpr int PIPE_LANES = 3;
+constexpr int PIPE_STREAMS = 2 + 3 * (PIPE_LANES + 3);
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
 
@@ -408,8 +418,8 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     const int rows = B * NF;
     const int nsplit = attn_splits(B, 1);
     float* state = a.state;
-    for (auto& ps : e->pipe_streams)
-        if (!ps) CK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    for (int i = 0; i < PIPE_STREAMS; ++i)
+        if (!e->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&e->pipe_streams[i], cudaStreamNonBlocking));
     size_t ev_used = 0;
     auto next_event = [&](cudaEvent_t* out) -> int {
         if (ev_used == e->pipe_events.size()) {
@@ -421,17 +431,20 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         return 0;
     };
     auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {     // `to` continues after everything enqueued on `from`
+        if (from == to) return 0;
         cudaEvent_t ev;
         if (int rc = next_event(&ev)) return rc;
         CK(cudaEventRecord(ev, from));
         CK(cudaStreamWaitEvent(to, ev, 0));
         return 0;
     };
-    cudaStream_t sF = origin, sBack = e->pipe_streams[7];
-    cudaStream_t sA[3] = {e->pipe_streams[1], e->pipe_streams[3], e->pipe_streams[5]};
-    cudaStream_t sB[3] = {e->pipe_streams[2], e->pipe_streams[4], e->pipe_streams[6]};
-    // fork: bring the worker streams into the capture
-    for (int i = 1; i < 8; ++i)
+    // stream map: [0] front (= capture origin), [1] back, then per block: PIPE_LANES x A, B1, B2a, B2b
+    cudaStream_t sF = origin, sBack = e->pipe_streams[1];
+    auto sA = [&](int b, int lane) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + lane]; };
+    auto sB1 = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES]; };
+    auto sB2a = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES + 1]; };
+    auto sB2b = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES + 2]; };
+    for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
     for (int k = 0; k < K; ++k) {
         float* wsp = a.wsp + (int64_t)k * slot;
@@ -442,40 +455,43 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         const int xlen_k = a.pos_rel ? a.x_len : std::max(0, std::min(a.x_len - k * HOP, HOP + LOOKAHEAD));
         float* yk = a.pos_rel ? a.y : a.y + (int64_t)k * HOP;
         const int ylen_k = a.pos_rel ? a.y_len : std::max(0, std::min(a.y_len - k * HOP, HOP));
+        const int lane = k % PIPE_LANES;
         CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, xk, a.xbs, a.xcs, xlen_k, X, state, ss, e->w, 1,
                     a.pos_rel, a.emb, PRE, k));
-        if (int rc = edge(sF, sA[0])) return rc;
+        if (int rc = edge(sF, sA(0, lane))) return rc;
         for (int b = 0; b < 3; ++b) {
             const BlockWeights& W = e->bw[b];
+            cudaStream_t st_a = sA(b, lane);
             GemmArgs g{};
             g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
             g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
-            CK(launch_rows_gemm(g, sA[b], false));
+            CK(launch_rows_gemm(g, st_a, false));
             LstmArgs l{};
             l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
             l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
-            CK(launch_lstm_rec(l, sA[b], false));
-            if (int rc = edge(sA[b], sB[b])) return rc;
-            CK(launch_k(false, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, sB[b], (const float*)Y, X,
+            CK(launch_lstm_rec(l, st_a, false));
+            if (int rc = edge(st_a, sB1(b))) return rc;
+            CK(launch_k(false, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, sB1(b), (const float*)Y, X,
                         QKVRAW, state, ss, b, W));
-            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sB[b], (const float*)X, (const float*)QKVRAW,
+            if (int rc = edge(sB1(b), sB2a(b))) return rc;
+            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sB2a(b), (const float*)X, (const float*)QKVRAW,
                         Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
             if (nsplit > 1) {
-                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sB[b],
+                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sB2a(b),
                                   (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1));
             } else {
-                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sB[b], (const float*)Q, (const float*)nullptr,
+                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sB2a(b), (const float*)Q, (const float*)nullptr,
                             (const float*)nullptr, (const float*)state, ss, b, Z, (float*)nullptr, 1, 1));
             }
-            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sB[b], (const float*)Z, X, (const float*)state, ss,
+            if (int rc = edge(sB2a(b), sB2b(b))) return rc;
+            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sB2b(b), (const float*)Z, X, (const float*)state, ss,
                         W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
-            if (int rc = edge(sB[b], b < 2 ? sA[b + 1] : sBack)) return rc;
+            if (int rc = edge(sB2b(b), b < 2 ? sA(b + 1, lane) : sBack)) return rc;
         }
         CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, yk, a.ybs, a.ycs, ylen_k, state, ss,
                     e->w, 1, a.pos_rel, k, K));
     }
-    // join
-    for (int i = 1; i < 8; ++i)
+    for (int i = 1; i < PIPE_STREAMS; ++i)                             // join
         if (int rc = edge(e->pipe_streams[i], origin)) return rc;
     return 0;
 }

@@ -499,6 +499,96 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
     if (nsplit > 1 && tid == 0) { pr[V_DIM] = mx; pr[V_DIM + 1] = lsum; }
 }
 
+// K4b'' query-tiled local attention for multi-frame calls: consecutive queries share 49 of their 50
+// window rows, so one CTA serves ATT_TQ consecutive queries of a (stream, head) from ONE pass over the
+// ATT_TQ + 49 rows of the linear K/V scratch: ~7x less L2 traffic than one CTA per query.
+// grid (ceil(T/ATT_TQ), 4, B), 256 threads (8 warps = 8 queries in the softmax phase).
+constexpr int ATT_TQ = 8;
+constexpr int ATT_TR = ATT_TQ + ATT - 1;        // 57 rows per tile
+
+__global__ void __launch_bounds__(256)
+attn_tile_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
+                 float* __restrict__ Z, int T) {
+    __shared__ __align__(16) float qs[ATT_TQ][QK_LD];    // 18.7 KB
+    __shared__ float sc[ATT_TQ][ATT_TR + 3];             // scores / probabilities, [query][tile row]
+    griddep_launch();
+    griddep_wait();
+    const int t0 = blockIdx.x * ATT_TQ, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    const int nq = min(ATT_TQ, T - t0);
+    const int64_t bh = (int64_t)b * NHEAD + h;
+    const float* kb = Kall + (bh * (ATT - 1 + T) + t0) * QK_LD;       // tile row r = scratch row t0 + r
+    const float* vb = Vall + (bh * (ATT - 1 + T) + t0) * V_DIM;
+    const int nrow = nq + ATT - 1;
+    for (int i = tid; i < ATT_TQ * (QK_LD / 4); i += 256) {
+        const int qi = i / (QK_LD / 4), c4 = i % (QK_LD / 4);
+        reinterpret_cast<float4*>(&qs[qi][0])[c4] =
+            (qi < nq) ? reinterpret_cast<const float4*>(Qbuf + (bh * T + t0 + qi) * QK_LD)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const float scale = rsqrtf((float)QK_DIM);
+    for (int r = warp; r < nrow; r += 8) {           // one warp per key row, dotted with all queries that see it
+        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)r * QK_LD);
+        float4 kv[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = lane + 32 * u;
+            kv[u] = (i < QK_LD / 4) ? kr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int qi = 0; qi < ATT_TQ; ++qi) {
+            // query qi sees tile rows qi .. qi+49
+            if (qi < nq && r >= qi && r < qi + ATT) {          // warp-uniform
+                float s = 0.f;
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int i = lane + 32 * u;
+                    if (i < QK_LD / 4) {
+                        const float4 qv = reinterpret_cast<const float4*>(&qs[qi][0])[i];
+                        s += kv[u].x * qv.x + kv[u].y * qv.y + kv[u].z * qv.z + kv[u].w * qv.w;
+                    }
+                }
+                s = warp_sum(s);
+                if (lane == 0) sc[qi][r] = s * scale;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < nq) {                                 // softmax of query `warp` over its 50 rows
+        const int qi = warp;
+        const float a0 = sc[qi][qi + lane];
+        const float a1 = (lane + 32 < ATT) ? sc[qi][qi + lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(a0, a1));
+        const float e0 = __expf(a0 - mx);
+        const float e1 = (lane + 32 < ATT) ? __expf(a1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        sc[qi][qi + lane] = e0 * inv;
+        if (lane + 32 < ATT) sc[qi][qi + lane + 32] = e1 * inv;
+    }
+    __syncthreads();
+    for (int c4 = tid; c4 < V_DIM / 4; c4 += 256) {
+        float4 acc[ATT_TQ];
+#pragma unroll
+        for (int qi = 0; qi < ATT_TQ; ++qi) acc[qi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < nrow; ++r) {
+            const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)r * V_DIM)[c4];
+#pragma unroll
+            for (int qi = 0; qi < ATT_TQ; ++qi) {
+                if (r >= qi && r < qi + ATT) {       // uniform across the CTA
+                    const float p = sc[qi][r];
+                    acc[qi].x = fmaf(p, v.x, acc[qi].x); acc[qi].y = fmaf(p, v.y, acc[qi].y);
+                    acc[qi].z = fmaf(p, v.z, acc[qi].z); acc[qi].w = fmaf(p, v.w, acc[qi].w);
+                }
+            }
+        }
+        const int f = c4 >> 2, c0 = (c4 & 3) * 4;
+#pragma unroll
+        for (int qi = 0; qi < ATT_TQ; ++qi)
+            if (qi < nq)
+                *reinterpret_cast<float4*>(Z + (((int64_t)b * T + t0 + qi) * NF + f) * CH + h * VD + c0) = acc[qi];
+    }
+}
+
 // K4b' cluster attention for few frames in flight: the 50-row window of one (stream, frame, head) is
 // split over a thread-block CLUSTER of 8 CTAs (8 SMs); every CTA reduces its rows to an
 // un-normalised partial (max, sum, o[1552]) in its own shared memory, then the cluster merges the
