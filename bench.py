@@ -278,7 +278,9 @@ def main():
 
     nl = ctypes.c_int32()
     _cabi.check(L.l2h_sep_launches_per_forward(net._engine(), cpc, ctypes.byref(nl)))
-    launches_per_step = 2 + n_calls * nl.value                   # state init + clip base + chains
+    pf = net.pipeline_frames() if cpc == 1 else 1
+    n_groups = (n_calls + pf - 1) // pf if pf > 1 else 0             # one header-advance kernel per pipelined graph
+    launches_per_step = 2 + n_calls * nl.value + n_groups        # state init + clip base + chains
 
     extras = {}
     roof = None

@@ -306,7 +306,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
     CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
-                a.pos_rel, emb, PRE, 0));
+                a.pos_rel, emb, PRE, 0, 1, 0));
     MARK("front");
     if (int rc = do_tap()) return rc;
 
@@ -383,7 +383,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (int rc = do_tap()) return rc;
     }
     CK(launch_k(pdl, back_kernel, dim3(T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
-                a.pos_rel, 0, 1));
+                a.pos_rel, 0, 1, 0, (int64_t)0));
     MARK("back");
 #undef MARK
     return 0;
@@ -403,8 +403,12 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
 constexpr int PIPE_MAX_FRAMES = 100;
-constexpr int PIPE_LANES = 3;
-constexpr int PIPE_STREAMS = 2 + 3 * (PIPE_LANES + 3);
+constexpr int PIPE_LANES = 3;      // hops of stage A (BiLSTM) in flight per block
+constexpr int PIPE_FLANES = 2;     // front_kernel lanes (frames of a group do not depend on each other there)
+constexpr int PIPE_BLANES = 3;     // back_kernel lanes
+constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
+constexpr int PIPE_STREAMS = PIPE_BASE + 3 * (PIPE_LANES + 3);
+static_assert(PIPE_STREAMS <= 32, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
 
@@ -438,26 +442,26 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         CK(cudaStreamWaitEvent(to, ev, 0));
         return 0;
     };
-    // stream map: [0] front (= capture origin), [1] back, then per block: PIPE_LANES x A, B1, B2a, B2b
-    cudaStream_t sF = origin, sBack = e->pipe_streams[1];
-    auto sA = [&](int b, int lane) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + lane]; };
-    auto sB1 = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES]; };
-    auto sB2a = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES + 1]; };
-    auto sB2b = [&](int b) { return e->pipe_streams[2 + b * (PIPE_LANES + 3) + PIPE_LANES + 2]; };
+    // stream map: [0] capture origin (fork / join / header advance), front lanes, back lanes, then per block:
+    // PIPE_LANES x A, B1, B2a, B2b
+    auto sFront = [&](int k) { return e->pipe_streams[1 + k % PIPE_FLANES]; };
+    auto sBackL = [&](int k) { return e->pipe_streams[1 + PIPE_FLANES + k % PIPE_BLANES]; };
+    auto sA = [&](int b, int lane) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + lane]; };
+    auto sB1 = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES]; };
+    auto sB2a = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES + 1]; };
+    auto sB2b = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES + 2]; };
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
     for (int k = 0; k < K; ++k) {
         float* wsp = a.wsp + (int64_t)k * slot;
         float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
         float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW; float* PRE = a.wsp + ws.PRE;   // PRE: front stream only
-        // x / y: either clip-relative addressing on the device (pos_rel) or a host-computed chunk offset
-        const float* xk = a.pos_rel ? a.x : a.x + (int64_t)k * HOP;
-        const int xlen_k = a.pos_rel ? a.x_len : std::max(0, std::min(a.x_len - k * HOP, HOP + LOOKAHEAD));
-        float* yk = a.pos_rel ? a.y : a.y + (int64_t)k * HOP;
-        const int ylen_k = a.pos_rel ? a.y_len : std::max(0, std::min(a.y_len - k * HOP, HOP));
+        // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip position
+        // the device derives from the state header)
         const int lane = k % PIPE_LANES;
-        CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, xk, a.xbs, a.xcs, xlen_k, X, state, ss, e->w, 1,
-                    a.pos_rel, a.emb, PRE, k));
+        cudaStream_t sF = sFront(k), sBack = sBackL(k);
+        CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs, a.x_len, X, state, ss, e->w, 1,
+                    a.pos_rel, a.emb, PRE, k, K, k * HOP));
         if (int rc = edge(sF, sA(0, lane))) return rc;
         for (int b = 0; b < 3; ++b) {
             const BlockWeights& W = e->bw[b];
@@ -488,11 +492,13 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                         W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
             if (int rc = edge(sB2b(b), b < 2 ? sA(b + 1, lane) : sBack)) return rc;
         }
-        CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, yk, a.ybs, a.ycs, ylen_k, state, ss,
-                    e->w, 1, a.pos_rel, k, K));
+        CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state,
+                    ss, e->w, 1, a.pos_rel, k, K, k * HOP, slot));
     }
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // join
         if (int rc = edge(e->pipe_streams[i], origin)) return rc;
+    advance_header_kernel<<<1, 1, 0, origin>>>(state, K);                // pos += K, ncalls += 1: after every hop of the group
+    CK(cudaGetLastError());
     return 0;
 }
 

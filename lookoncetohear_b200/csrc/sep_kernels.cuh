@@ -62,6 +62,12 @@ __global__ void state_init_kernel(float* state, int64_t total_floats, int64_t st
     }
 }
 
+__global__ void advance_header_kernel(float* state, int frames) {
+    StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
+    hdr->pos += frames;
+    hdr->ncalls += 1;
+}
+
 __global__ void set_clip_base_kernel(float* state) {
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     hdr->clip_base = hdr->pos;
@@ -79,7 +85,8 @@ __device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len,
              float* __restrict__ X, float* __restrict__ state, int64_t sstride, SepWeights w, int T,
-             int pos_rel, const float* __restrict__ emb, float* __restrict__ spk_pre, int frame_k) {
+             int pos_rel, const float* __restrict__ emb, float* __restrict__ spk_pre, int frame_k, int frames_total,
+             int sample_off) {
     extern __shared__ __align__(16) float wat_s[];     // [192][196]
     __shared__ __align__(16) float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
@@ -97,17 +104,21 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     __syncthreads();
     tma_load_split(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar, tid, 256);     // 74 bulk copies in flight
     griddep_wait();
-    // frame_k: index of this one-frame call inside a pipelined multi-frame graph (0 otherwise); the
-    // header is advanced once, by the last frame of the graph
+    // A "group" is what advances the state header once: the T frames of an ordinary call, or the
+    // frames_total one-frame calls of a pipelined graph (frame_k = index inside it).  gi = frame index in
+    // the group.  All frames of a group read the tails the PREVIOUS group left (parity ncalls & 1) and
+    // recompute what they need of their predecessors inside the group; only the group's last frame writes
+    // the new tails (other parity) -- so the frames of a group never depend on each other here.
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
-    const int par = (int)((hdr->ncalls + frame_k) & 1);
+    const int par = (int)(hdr->ncalls & 1);
+    const int gi = frame_k + t, GN = (frames_total > 1) ? frames_total : T;
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* cb = st + ST_CONV + par * (2 * 4 * NF);
     float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
 
     for (int i = tid; i < 3 * 4 * 100; i += 256) (&U[0][0][0])[i] = 0.f;
     // pos_rel: x is a whole clip and this call starts at frame (pos - clip_base) of it
-    const int s0 = HOP * (t - 2) + (pos_rel ? (int)(hdr->pos - hdr->clip_base + frame_k) * HOP : 0);
+    const int s0 = HOP * (t - 2) + sample_off + (pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0);
     for (int i = tid; i < NMIC * 448; i += 256) {
         const int m = i / 448, n = i % 448, s = s0 + n;
         xs[m][n] = (s >= 0 && s < x_len) ? x[(int64_t)b * x_bstride + (int64_t)m * x_cstride + s] : 0.f;
@@ -115,9 +126,9 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     __syncthreads();
     // history frames from conv_buf: frame -2 -> slot 0, frame -1 -> slot 1
     for (int i = 0; i < 2; ++i) {
-        const int tt = t - 2 + i;
-        if (tt < 0)
-            for (int e = tid; e < 4 * NF; e += 256) U[i][e / NF][1 + e % NF] = cb[(2 + tt) * 4 * NF + e];
+        const int g = gi - 2 + i;               // frame index in the group; < 0: before the group -> conv_buf
+        if (g < 0)
+            for (int e = tid; e < 4 * NF; e += 256) U[i][e / NF][1 + e % NF] = cb[(2 + g) * 4 * NF + e];
     }
     if (tid < NROW) {
         float acc[3][NMIC];
@@ -136,7 +147,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
         const int ri = tid / NF, f = tid % NF;      // rows 0..96 real, 97..193 imaginary
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            if (t - 2 + i >= 0) {                   // channels: [Re m0, Re m1, Im m0, Im m1]
+            if (gi - 2 + i >= 0) {                  // channels: [Re m0, Re m1, Im m0, Im m1]
                 U[i][ri * 2 + 0][1 + f] = acc[i][0];
                 U[i][ri * 2 + 1][1 + f] = acc[i][1];
             }
@@ -161,15 +172,12 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
             X[(((int64_t)b * T + t) * NF + f) * CH + o] = acc;
         }
     }
-    // next conv_buf = spectrogram rows of the last two frames of this call
-    if (T == 1) {
+    // next conv_buf = spectrogram rows of the last two frames of the group, written by its last frame
+    if (gi == GN - 1) {
         for (int e = tid; e < 4 * NF; e += 256) {
             cb_next[e] = U[1][e / NF][1 + e % NF];
             cb_next[4 * NF + e] = U[2][e / NF][1 + e % NF];
         }
-    } else if (t >= T - 2) {
-        const int slot = t - (T - 2);
-        for (int e = tid; e < 4 * NF; e += 256) cb_next[slot * 4 * NF + e] = U[2][e / NF][1 + e % NF];
     }
 }
 
@@ -866,7 +874,7 @@ static_assert(BACK_WS_HALF * NFFT <= 4 * 99 * 64, "filter half must fit in the f
 __global__ void __launch_bounds__(256)
 back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
             int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int frame_k,
-            int frames_total) {
+            int frames_total, int sample_off, int64_t hist_stride) {
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]; later: filter halves
     float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
@@ -875,11 +883,15 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     griddep_launch();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    // group bookkeeping as in front_kernel: gi = frame index in the group, frames before the group come
+    // from the deconv tails the previous group left, frames inside it from X (T > 1) or from the
+    // workspace slots of the previous one-frame calls of the pipelined graph (hist_stride apart)
+    const int gi = frame_k + t, GN = (frames_total > 1) ? frames_total : T;
     // zero the frequency padding rows (0 and 98) of every slot and whole slots that stay empty
     for (int i = tid; i < 4 * 99 * 64; i += 256) {
         const int slot = i / (99 * 64), r = (i / 64) % 99;
-        const int tt = t - 3 + slot;
-        if (r == 0 || r == 98 || tt < -2) Xs[i] = 0.f;
+        const int g = gi - 3 + slot;
+        if (r == 0 || r == 98 || g < -2) Xs[i] = 0.f;
     }
     float wr[2][36];
     {
@@ -892,8 +904,8 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     __syncthreads();
     griddep_wait();
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
-    const int par = (int)((hdr->ncalls + frame_k) & 1);
-    const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base + frame_k) * HOP : 0;
+    const int par = (int)(hdr->ncalls & 1);
+    const int soff = sample_off + (pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0);
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* db = st + ST_DECONV + par * (2 * FC);
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
@@ -901,13 +913,16 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
     {
         int nfr = 0;
-        for (int slot = 0; slot < 4; ++slot) nfr += (t - 3 + slot >= -2) ? 1 : 0;
+        for (int slot = 0; slot < 4; ++slot) nfr += (gi - 3 + slot >= -2) ? 1 : 0;
         if (tid == 0) { fence_proxy_async(); mbar_expect_tx(&bars[0], nfr * FC * 4); }
         __syncthreads();
         for (int slot = 0; slot < 4; ++slot) {
-            const int tt = t - 3 + slot;
-            if (tt < -2) continue;
-            const float* src = (tt >= 0) ? X + ((int64_t)b * T + tt) * FC : db + (2 + tt) * FC;
+            const int g = gi - 3 + slot;
+            if (g < -2) continue;
+            const float* src;
+            if (g < 0) src = db + (2 + g) * FC;
+            else if (frames_total > 1) src = X - (int64_t)(3 - slot) * hist_stride + (int64_t)b * FC;   // slot of one-frame call g
+            else src = X + ((int64_t)b * T + (t - 3 + slot)) * FC;
             tma_load_split(Xs + (slot * 99 + 1) * 64, src, FC * 4, &bars[0], tid, 256);
         }
     }
@@ -915,7 +930,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     // deconv for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
     {
         const int warp = tid >> 5, lane = tid & 31;
-        for (int fi = (t >= 1 ? 0 : 1); fi < 2; ++fi) {
+        for (int fi = (gi >= 1 ? 0 : 1); fi < 2; ++fi) {
             for (int f = warp; f < NF; f += 8) {
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -939,18 +954,15 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
                 }
             }
         }
-        if (t == 0)
+        if (gi == 0)
             for (int i = tid; i < NSRC * NROW; i += 256) R[i] = ib[i];
     }
-    // next deconv tails come straight from the staged frames
-    if (T == 1) {
+    // next deconv tails (frames GN-2, GN-1) come straight from the staged frames of the group's last frame
+    if (gi == GN - 1) {
         for (int i = tid; i < FC / 4; i += 256) {
-            reinterpret_cast<float4*>(db_next)[i] = reinterpret_cast<const float4*>(Xs + (2 * 99 + 1) * 64)[i];       // frame -1
-            reinterpret_cast<float4*>(db_next + FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];  // frame 0
+            reinterpret_cast<float4*>(db_next)[i] = reinterpret_cast<const float4*>(Xs + (2 * 99 + 1) * 64)[i];
+            reinterpret_cast<float4*>(db_next + FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];
         }
-    } else if (t >= T - 2) {
-        for (int i = tid; i < FC / 4; i += 256)
-            reinterpret_cast<float4*>(db_next + (t - (T - 2)) * FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];
     }
     __syncthreads();                        // R complete; nobody reads the frame region any more
     // synthesis: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}; filters streamed in two halves
@@ -990,17 +1002,17 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
             y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
         }
     }
-    if (t == T - 1)
+    if (gi == GN - 1)
         for (int i = tid; i < NSRC * NROW; i += 256) ib_next[i] = R[NSRC * NROW + i];
     __syncthreads();
-    if (tid == 0) {
+    // ordinary call: the last CTA to finish advances the header (a pipelined graph runs several back_kernels
+    // at once and advances it with advance_header_kernel after all of its frames instead)
+    if (frames_total == 1 && tid == 0) {
         __threadfence();
         const int prev = atomicAdd(&hdr->done, 1);
         if (prev == (int)(gridDim.x * gridDim.y) - 1) {
-            if (frame_k == frames_total - 1) {      // the last frame of a (possibly pipelined) group advances the header
-                hdr->pos += (long long)T * frames_total;
-                hdr->ncalls += frames_total;
-            }
+            hdr->pos += T;
+            hdr->ncalls += 1;
             hdr->done = 0;
             __threadfence();
         }
