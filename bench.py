@@ -385,9 +385,10 @@ def main():
             "config": {"workload": "streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); "
                                    "4 s clip = 500 hops per step, fresh state per step",
                        "chunks_per_call": cpc,
-                       "pipeline": "wavefront over (block, hop): up to %d one-hop chains per CUDA graph on 8 streams; every hop "
-                                   "is its own T=1 chain with the state carried (frames_per_s_unpipelined / chunk_latency_us "
-                                   "give the strictly sequential figures)" % net.pipeline_frames(),
+                       "pipeline": "wavefront over (block, hop) stages: up to %d one-hop chains per multi-stream CUDA graph; every "
+                                   "hop is its own T=1 kernel chain with the state carried hop to hop, results bit-identical to the "
+                                   "sequential run (frames_per_s_unpipelined / chunk_latency_us give the strictly sequential "
+                                   "figures)" % net.pipeline_frames(),
                        "parallelism": f"dp{world} (independent streams, weights broadcast over NCCL)",
                        "l2": "flushed (256 MiB write) between timed iterations"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_calls * 2 * (HOP * cpc + 64) * 4,

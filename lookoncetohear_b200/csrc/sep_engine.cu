@@ -59,6 +59,8 @@ struct SepEngine {
     cudaStream_t cap_stream = nullptr;
     cudaStream_t pipe_streams[32] = {};
     std::vector<cudaEvent_t> pipe_events;
+    int pipe_frames = 100;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
+    int pipe_alanes = 3;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES_MAX)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
@@ -369,7 +371,8 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
                               (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T));
-        } else if (T >= 2 * ATT_TQ) {                // many frames: query-tiled, one pass over 57 rows serves 8 queries
+        } else if ((int64_t)B * NHEAD * ((T + ATT_TQ - 1) / ATT_TQ) >= 148) {   // enough tiles to fill the GPU: query-tiled,
+            // one pass over 57 rows serves 8 queries
             CK(launch_k(pdl, attn_tile_kernel, dim3((T + ATT_TQ - 1) / ATT_TQ, NHEAD, B), dim3(256), 0, st, (const float*)Q,
                         (const float*)KALL, (const float*)VALL, Z, T));
         } else {
@@ -403,7 +406,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
 constexpr int PIPE_MAX_FRAMES = 100;
-constexpr int PIPE_LANES = 3;      // hops of stage A (BiLSTM) in flight per block
+constexpr int PIPE_LANES = 4;      // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
 constexpr int PIPE_FLANES = 2;     // front_kernel lanes (frames of a group do not depend on each other there)
 constexpr int PIPE_BLANES = 3;     // back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
@@ -458,7 +461,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW; float* PRE = a.wsp + ws.PRE;   // PRE: front stream only
         // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip position
         // the device derives from the state header)
-        const int lane = k % PIPE_LANES;
+        const int lane = k % e->pipe_alanes;
         cudaStream_t sF = sFront(k), sBack = sBackL(k);
         CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs, a.x_len, X, state, ss, e->w, 1,
                     a.pos_rel, a.emb, PRE, k, K, k * HOP));
@@ -712,7 +715,7 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
     int group = cpc;
     if (pipe) {
         const int64_t slot = pipe_slot_floats(e, batch);
-        group = (int)std::min<int64_t>(std::min(PIPE_MAX_FRAMES, n_calls), (int64_t)(ws_bytes / sizeof(float)) / slot);
+        group = (int)std::min<int64_t>(std::min(e->pipe_frames, n_calls), (int64_t)(ws_bytes / sizeof(float)) / slot);
         if (group < 2) group = 1;
     }
     const int hops_total = n_calls * cpc;
@@ -752,7 +755,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
     if (cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1) {
         // groups of up to PIPE_MAX_FRAMES one-frame calls, each group one wavefront-pipelined graph
         const int64_t slot = pipe_slot_floats(e, batch);
-        int kmax = (int)std::min<int64_t>(PIPE_MAX_FRAMES, (int64_t)(ws_bytes / sizeof(float)) / slot);
+        int kmax = (int)std::min<int64_t>(e->pipe_frames, (int64_t)(ws_bytes / sizeof(float)) / slot);
         if (kmax >= 2) {
             int done = 0;
             while (done < n_calls) {
@@ -784,6 +787,8 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     if (!e || !name) return fail(1, "bad argument");
     const std::string n(name);
     if (n == "pipeline") e->use_pipe = value != 0;
+    else if (n == "pipeline_frames") e->pipe_frames = std::max(2, std::min(PIPE_MAX_FRAMES, (int)value));
+    else if (n == "pipeline_lanes") e->pipe_alanes = std::max(1, std::min(PIPE_LANES, (int)value));
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
     else return fail(2, "unknown option: " + n);

@@ -578,14 +578,22 @@ attn_tile_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall,
         float4 acc[ATT_TQ];
 #pragma unroll
         for (int qi = 0; qi < ATT_TQ; ++qi) acc[qi] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < nrow; ++r) {
-            const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)r * V_DIM)[c4];
+        for (int r0 = 0; r0 < nrow; r0 += 8) {       // 8 value rows in flight per thread
+            float4 v[8];
 #pragma unroll
-            for (int qi = 0; qi < ATT_TQ; ++qi) {
-                if (r >= qi && r < qi + ATT) {       // uniform across the CTA
-                    const float p = sc[qi][r];
-                    acc[qi].x = fmaf(p, v.x, acc[qi].x); acc[qi].y = fmaf(p, v.y, acc[qi].y);
-                    acc[qi].z = fmaf(p, v.z, acc[qi].z); acc[qi].w = fmaf(p, v.w, acc[qi].w);
+            for (int u = 0; u < 8; ++u)
+                v[u] = (r0 + u < nrow) ? reinterpret_cast<const float4*>(vb + (int64_t)(r0 + u) * V_DIM)[c4]
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+#pragma unroll
+                for (int qi = 0; qi < ATT_TQ; ++qi) {
+                    if (r < nrow && r >= qi && r < qi + ATT) {       // uniform across the CTA
+                        const float p = sc[qi][r];
+                        acc[qi].x = fmaf(p, v[u].x, acc[qi].x); acc[qi].y = fmaf(p, v[u].y, acc[qi].y);
+                        acc[qi].z = fmaf(p, v[u].z, acc[qi].z); acc[qi].w = fmaf(p, v[u].w, acc[qi].w);
+                    }
                 }
             }
         }
