@@ -59,7 +59,7 @@ struct SepEngine {
     cudaStream_t cap_stream = nullptr;
     cudaStream_t pipe_streams[32] = {};
     std::vector<cudaEvent_t> pipe_events;
-    int pipe_frames = 100;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
+    int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
     int pipe_alanes = 3;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES_MAX)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
@@ -370,14 +370,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         MARK("qkv");
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
-                              (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T));
+                              (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T, 0));
         } else if ((int64_t)B * NHEAD * ((T + ATT_TQ - 1) / ATT_TQ) >= 148) {   // enough tiles to fill the GPU: query-tiled,
             // one pass over 57 rows serves 8 queries
             CK(launch_k(pdl, attn_tile_kernel, dim3((T + ATT_TQ - 1) / ATT_TQ, NHEAD, B), dim3(256), 0, st, (const float*)Q,
                         (const float*)KALL, (const float*)VALL, Z, T));
         } else {
             CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
-                        (const float*)VALL, (const float*)state, ss, b, Z, PART, 1, T));
+                        (const float*)VALL, (const float*)state, ss, b, Z, PART, 1, T, 0));
         }
         MARK("attn");
         CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
@@ -405,12 +405,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // workspace slot; state addressing uses pos + frame_k / parity(ncalls + frame_k); the header advances once,
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
-constexpr int PIPE_MAX_FRAMES = 100;
+constexpr int PIPE_MAX_FRAMES = 250;
 constexpr int PIPE_LANES = 4;      // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
 constexpr int PIPE_FLANES = 2;     // front_kernel lanes (frames of a group do not depend on each other there)
 constexpr int PIPE_BLANES = 3;     // back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
-constexpr int PIPE_STREAMS = PIPE_BASE + 3 * (PIPE_LANES + 3);
+constexpr int PIPE_PER_BLOCK = PIPE_LANES + 4;     // A lanes, B1 (mid), Bq (qkv), Ba (attention), Bo (attn_out)
+constexpr int PIPE_STREAMS = PIPE_BASE + 3 * PIPE_PER_BLOCK;
+constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites a ring row hop t's attention still reads
 static_assert(PIPE_STREAMS <= 32, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
@@ -449,10 +451,13 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     // PIPE_LANES x A, B1, B2a, B2b
     auto sFront = [&](int k) { return e->pipe_streams[1 + k % PIPE_FLANES]; };
     auto sBackL = [&](int k) { return e->pipe_streams[1 + PIPE_FLANES + k % PIPE_BLANES]; };
-    auto sA = [&](int b, int lane) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + lane]; };
-    auto sB1 = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES]; };
-    auto sB2a = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES + 1]; };
-    auto sB2b = [&](int b) { return e->pipe_streams[PIPE_BASE + b * (PIPE_LANES + 3) + PIPE_LANES + 2]; };
+    auto sA = [&](int b, int lane) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + lane]; };
+    auto sB1 = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES]; };
+    auto sBq = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1]; };
+    auto sBa = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 2]; };
+    auto sB2b = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 3]; };
+    // attention-done events of the last PIPE_QKV_AHEAD+1 hops per block (ring write-after-read guard)
+    std::vector<std::vector<cudaEvent_t>> att_done(3, std::vector<cudaEvent_t>(K, nullptr));
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
     for (int k = 0; k < K; ++k) {
@@ -480,17 +485,23 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
             if (int rc = edge(st_a, sB1(b))) return rc;
             CK(launch_k(false, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, sB1(b), (const float*)Y, X,
                         QKVRAW, state, ss, b, W));
-            if (int rc = edge(sB1(b), sB2a(b))) return rc;
-            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sB2a(b), (const float*)X, (const float*)QKVRAW,
-                        Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
-            if (nsplit > 1) {
-                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sB2a(b),
-                                  (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1));
-            } else {
-                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sB2a(b), (const float*)Q, (const float*)nullptr,
-                            (const float*)nullptr, (const float*)state, ss, b, Z, (float*)nullptr, 1, 1));
+            if (int rc = edge(sB1(b), sBq(b))) return rc;
+            if (k >= PIPE_QKV_AHEAD + 1) {          // the row this hop's K/V overwrite: attention of hop k-3 must be done
+                CK(cudaStreamWaitEvent(sBq(b), att_done[b][k - PIPE_QKV_AHEAD - 1], 0));
             }
-            if (int rc = edge(sB2a(b), sB2b(b))) return rc;
+            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sBq(b), (const float*)X, (const float*)QKVRAW,
+                        Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
+            if (int rc = edge(sBq(b), sBa(b))) return rc;
+            if (nsplit > 1) {
+                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sBa(b),
+                                  (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
+            } else {
+                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sBa(b), (const float*)Q, (const float*)nullptr,
+                            (const float*)nullptr, (const float*)state, ss, b, Z, (float*)nullptr, 1, 1, k));
+            }
+            if (int rc = next_event(&att_done[b][k])) return rc;
+            CK(cudaEventRecord(att_done[b][k], sBa(b)));
+            CK(cudaStreamWaitEvent(sB2b(b), att_done[b][k], 0));
             CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sB2b(b), (const float*)Z, X, (const float*)state, ss,
                         W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
             if (int rc = edge(sB2b(b), b < 2 ? sA(b + 1, lane) : sBack)) return rc;

@@ -241,10 +241,10 @@ __global__ void kv_gather_kernel(const float* __restrict__ state, int64_t sstrid
     const int i = blockIdx.x, bh = blockIdx.y, b = bh / NHEAD, h = bh % NHEAD;
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const long long fr = hdr->pos - (ATT - 1) + i;
-    const int slot = (int)(((fr % ATT) + ATT) % ATT);
+    const int slot = (int)(((fr % RING) + RING) % RING);
     const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-    const float4* ks = reinterpret_cast<const float4*>(sb + BK_K + ((int64_t)h * ATT + slot) * QK_LD);
-    const float4* vs = reinterpret_cast<const float4*>(sb + BK_V + ((int64_t)h * ATT + slot) * V_DIM);
+    const float4* ks = reinterpret_cast<const float4*>(sb + BK_K + ((int64_t)h * RING + slot) * QK_LD);
+    const float4* vs = reinterpret_cast<const float4*>(sb + BK_V + ((int64_t)h * RING + slot) * V_DIM);
     float4* kd = reinterpret_cast<float4*>(Kall + ((int64_t)bh * (ATT - 1 + T) + i) * QK_LD);
     float4* vd = reinterpret_cast<float4*>(Vall + ((int64_t)bh * (ATT - 1 + T) + i) * V_DIM);
     const bool live = fr >= 0;
@@ -379,9 +379,9 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
         dst0 = Qbuf + (bh * T + t) * QK_LD;
     } else {
         float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-        const int slot = (int)((pos + t) % ATT);
+        const int slot = (int)((pos + t) % RING);
         if (t >= T - ATT)
-            dst1 = sb + (which == 1 ? BK_K : BK_V) + ((int64_t)h * ATT + slot) * ld;
+            dst1 = sb + (which == 1 ? BK_K : BK_V) + ((int64_t)h * RING + slot) * ld;
         if (T > 1) dst0 = (which == 1 ? Kall : Vall) + (bh * (ATT - 1 + T) + (ATT - 1) + t) * ld;
     }
     {
@@ -412,7 +412,7 @@ constexpr int PART_LD = V_DIM + 4;      // [o (1552) | m | l | pad pad]
 __global__ void __launch_bounds__(256)
 attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
             const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z,
-            float* __restrict__ part, int nsplit, int T) {
+            float* __restrict__ part, int nsplit, int T, int frame_k) {
     __shared__ __align__(16) float qs[QK_LD];
     __shared__ float sc[64];
     griddep_launch();
@@ -423,16 +423,18 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
     const int64_t bh = (int64_t)b * NHEAD + h;
     const float* kb;
     const float* vb;
-    if (T == 1) {
+    int first = j0, wrap = 0x7fffffff;      // window row j -> storage row (first + j) % wrap
+    if (T == 1) {                           // ring: window = frames pos-49 .. pos, frame n lives in slot n mod RING
         const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-        kb = sb + BK_K + (int64_t)h * ATT * QK_LD;
-        vb = sb + BK_V + (int64_t)h * ATT * V_DIM;
+        kb = sb + BK_K + (int64_t)h * RING * QK_LD;
+        vb = sb + BK_V + (int64_t)h * RING * V_DIM;
+        const long long p0 = reinterpret_cast<const StateHeader*>(state)->pos + frame_k - (ATT - 1) + j0;
+        first = (int)(((p0 % RING) + RING) % RING);
+        wrap = RING;
     } else {
         kb = Kall + (bh * (ATT - 1 + T) + t) * QK_LD;
         vb = Vall + (bh * (ATT - 1 + T) + t) * V_DIM;
     }
-    kb += (int64_t)j0 * QK_LD;
-    vb += (int64_t)j0 * V_DIM;
     const float* q = Qbuf + (bh * T + t) * QK_LD;
     for (int i = tid; i < QK_LD / 4; i += 256)
         reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(q)[i];
@@ -440,7 +442,7 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
     const int warp = tid >> 5, lane = tid & 31;
     const float scale = rsqrtf((float)QK_DIM);
     for (int j = warp; j < nr; j += 8) {
-        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)j * QK_LD);
+        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)((first + j) % wrap) * QK_LD);
         float4 kv[5];
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
@@ -481,7 +483,8 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
             float4 v[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j)
-                v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % wrap) * V_DIM)[c4]
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const float p = (j < nr) ? sc[j] : 0.f;
@@ -491,7 +494,7 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
         } else {
 #pragma unroll 10
             for (int j = 0; j < nr; ++j) {
-                const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4];
+                const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % wrap) * V_DIM)[c4];
                 const float p = sc[j];
                 acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
                 acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
@@ -615,7 +618,8 @@ constexpr int ATT_CL = 8;
 
 __global__ void __launch_bounds__(256)
 attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
-                    const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T) {
+                    const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T,
+                    int frame_k) {
     namespace cg = cooperative_groups;
     __shared__ __align__(16) float qs[QK_LD];
     __shared__ __align__(16) float os[V_DIM];     // this CTA's partial output
@@ -631,16 +635,18 @@ attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Ka
     const int64_t bh = (int64_t)b * NHEAD + h;
     const float* kb;
     const float* vb;
-    if (T == 1) {
+    int first = j0, wrap = 0x7fffffff;      // window row j -> storage row (first + j) % wrap
+    if (T == 1) {                           // ring: window = frames pos-49 .. pos, frame n lives in slot n mod RING
         const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-        kb = sb + BK_K + (int64_t)h * ATT * QK_LD;
-        vb = sb + BK_V + (int64_t)h * ATT * V_DIM;
+        kb = sb + BK_K + (int64_t)h * RING * QK_LD;
+        vb = sb + BK_V + (int64_t)h * RING * V_DIM;
+        const long long p0 = reinterpret_cast<const StateHeader*>(state)->pos + frame_k - (ATT - 1) + j0;
+        first = (int)(((p0 % RING) + RING) % RING);
+        wrap = RING;
     } else {
         kb = Kall + (bh * (ATT - 1 + T) + t) * QK_LD;
         vb = Vall + (bh * (ATT - 1 + T) + t) * V_DIM;
     }
-    kb += (int64_t)j0 * QK_LD;
-    vb += (int64_t)j0 * V_DIM;
     const float* q = Qbuf + (bh * T + t) * QK_LD;
     for (int i = tid; i < QK_LD / 4; i += 256)
         reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(q)[i];
@@ -648,7 +654,7 @@ attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Ka
     const int warp = tid >> 5, lane = tid & 31;
     const float scale = rsqrtf((float)QK_DIM);
     if (warp < nr) {                               // one warp per key row (nr <= 7)
-        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)warp * QK_LD);
+        const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)((first + warp) % wrap) * QK_LD);
         float4 kv[5];
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
@@ -681,7 +687,8 @@ attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Ka
         float4 v[7];
 #pragma unroll
         for (int j = 0; j < 7; ++j)
-            v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)j * V_DIM)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % wrap) * V_DIM)[c4]
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 7; ++j) {

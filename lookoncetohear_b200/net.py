@@ -121,8 +121,9 @@ class SepState(dict):
     _ST_DECONV = _ST_CONV + 2 * 2 * 4 * 97
     _ST_ISTFT = _ST_DECONV + 2 * 2 * 6208
     _ST_BLK = _ST_ISTFT + 2 * 2 * 194
-    _BK_V = 4 * 50 * 584
-    _BK_H = _BK_V + 4 * 50 * 1552
+    _RING = 52                      # K/V ring slots per head (csrc/sep_layout.h)
+    _BK_V = 4 * 52 * 584
+    _BK_H = _BK_V + 4 * 52 * 1552
     _BK_C = _BK_H + 6208
     _BK_STRIDE = _BK_C + 6208
 
@@ -137,14 +138,14 @@ class SepState(dict):
         out = dict(conv_buf=conv.permute(0, 2, 1, 3).contiguous(),
                    deconv_buf=deconv.permute(0, 3, 1, 2).contiguous(),
                    istft_buf=istft.unsqueeze(-1).contiguous(), gridnet_bufs={})
-        # ring slot of frame n is n % 50; history rows are frames pos-49 .. pos-1
+        # ring slot of frame n is n % 52; history rows are frames pos-49 .. pos-1
         frames = torch.arange(pos - 49, pos)
-        slots = torch.remainder(frames, 50).to(self.buf.device)
+        slots = torch.remainder(frames, self._RING).to(self.buf.device)
         live = (frames >= 0).to(self.buf.device, self.buf.dtype)[None, None, :, None]
         for i in range(self.n_blocks):
             o = self._ST_BLK + i * self._BK_STRIDE
-            K = r[:, o:o + self._BK_V].view(B, 4, 50, 584)[:, :, :, :582]
-            V = r[:, o + self._BK_V:o + self._BK_H].view(B, 4, 50, 1552)
+            K = r[:, o:o + self._BK_V].view(B, 4, self._RING, 584)[:, :, :, :582]
+            V = r[:, o + self._BK_V:o + self._BK_H].view(B, 4, self._RING, 1552)
             out["gridnet_bufs"][f"buf{i}"] = dict(
                 K_buf=(K[:, :, slots] * live).reshape(B * 4, 49, 582).contiguous(),
                 V_buf=(V[:, :, slots] * live).reshape(B * 4, 49, 1552).contiguous(),
