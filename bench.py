@@ -182,8 +182,14 @@ def main():
     ap.add_argument("--chunks-per-call", type=int, default=1,
                     help="hops handed to the engine per call (1 = true chunk-by-chunk streaming)")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency / buffered-throughput extras")
+    ap.add_argument("--clip-hops", type=int, default=0,
+                    help="profiling aid: shorten the clip to this many hops (the default, 0, is the 4 s = 500-hop clip)")
     args = ap.parse_args()
 
+    global CLIP_SAMPLES, FRAMES
+    if args.clip_hops > 0:
+        FRAMES = args.clip_hops
+        CLIP_SAMPLES = FRAMES * HOP
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -383,7 +389,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": value / world / 125.0,
             "config": {"workload": "streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); "
-                                   "4 s clip = 500 hops per step, fresh state per step",
+                                   "%.1f s clip = %d hops per step, fresh state per step" % (FRAMES * 0.008, FRAMES),
                        "chunks_per_call": cpc,
                        "pipeline": "wavefront over (block, hop) stages: up to %d one-hop chains per multi-stream CUDA graph; every "
                                    "hop is its own T=1 kernel chain with the state carried hop to hop, results bit-identical to the "

@@ -60,7 +60,7 @@ struct SepEngine {
     cudaStream_t pipe_streams[32] = {};
     std::vector<cudaEvent_t> pipe_events;
     int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
-    int pipe_alanes = 3;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES_MAX)
+    int pipe_alanes = 4;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
