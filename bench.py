@@ -233,8 +233,10 @@ def main():
         st = net.init_buffers(1, dev)
         net.stream_dev(x_dev, emb, chunks_per_call=cpc, state=st, n_calls=n_calls, out=y_dev)
 
+    y_pin = torch.empty(1, 2, n_calls * HOP * cpc, dtype=torch.float32).pin_memory()
+
     def step_host():
-        return net.stream_host(x_pin, emb, chunks_per_call=cpc)
+        return net.stream_host(x_pin, emb, chunks_per_call=cpc, out=y_pin)
 
     def barrier():
         if world > 1:
@@ -282,6 +284,13 @@ def main():
     value = frames_total / (dev_ms * 1e-3)
     e2e_value = frames_total / (e2e_ms * 1e-3)
 
+    # host<->device bytes of one step through l2h_sep_stream_host (rounds of `hops_per_round` hops)
+    hops_per_round = max(cpc, net.pipeline_frames() if cpc == 1 else 1)
+    h2d_bytes = d2h_bytes = 0
+    for h0 in range(0, n_calls * cpc, hops_per_round):
+        hops = min(hops_per_round, n_calls * cpc - h0)
+        h2d_bytes += 2 * max(0, min(CLIP_SAMPLES - h0 * HOP, HOP * hops + 64)) * 4
+        d2h_bytes += 2 * max(0, min(CLIP_SAMPLES - h0 * HOP, HOP * hops)) * 4
     nl = ctypes.c_int32()
     _cabi.check(L.l2h_sep_launches_per_forward(net._engine(), cpc, ctypes.byref(nl)))
     pf = net.pipeline_frames() if cpc == 1 else 1
@@ -366,7 +375,11 @@ def main():
         alg = kernel_algorithmic_bytes(dom[0], cpc)
         ach = alg / (dom[1]["ms_mean"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": ach / pk["hbm_gbs"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed
+                # ncu --set full capture profiles/r01e_lstm_rec3_full.md (warm L2: the launch's 379 KB of
+                # algorithmic bytes are L2 hits; 0.9 KB read + 10.5 KB written reach DRAM)
+                "traffic": 11392.0 if dom[0] == "lstm_intra" else None, "peak_source": pk["source"],
                 "alg_bytes_per_launch": alg, "mean_us_per_launch": 1e3 * dom[1]["ms_mean"],
                 "share_of_chain": dom[1]["ms_total"] / sum(v["ms_total"] for v in prof.values()),
                 "note": "batch-1 streaming is latency-bound (serial LSTM chain, 13 MB working set resident in L2); "
@@ -397,9 +410,11 @@ def main():
                                    "figures)" % net.pipeline_frames(),
                        "parallelism": f"dp{world} (independent streams, weights broadcast over NCCL)",
                        "l2": "flushed (256 MiB write) between timed iterations"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_calls * 2 * (HOP * cpc + 64) * 4,
-                    "d2h_bytes_per_step": n_calls * 2 * HOP * cpc * 4, "rtf": e2e_value / world / 125.0,
-                    "api": "l2h_sep_stream_host (pinned host buffers, per-chunk cudaMemcpyAsync in the timed region)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "rtf": e2e_value / world / 125.0, "hops_per_round": hops_per_round,
+                    "api": "l2h_sep_stream_host: pinned host clip in, pinned host clip out; per round one cudaMemcpy2DAsync "
+                           "H2D of the round's samples, the one-hop kernel chains of the round, one D2H of its output -- all "
+                           "inside the timed region, fresh state per step"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "wall_s": t_wall,
         }

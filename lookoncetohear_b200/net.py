@@ -350,10 +350,12 @@ class Net(nn.Module):
         self._last_stream_state = state
         return y
 
-    def stream_host(self, x_host, embed_dev, chunks_per_call=1, state=None):
+    def stream_host(self, x_host, embed_dev, chunks_per_call=1, state=None, out=None):
         """End-to-end streaming with HOST buffers (l2h_sep_stream_host): x_host [B,M,N] CPU tensor
-        (pinned here if it is not), every call copies its chunk host->device, runs the chain and
-        copies the new samples back; returns y [B,S,128*n_calls*chunks_per_call] on the host."""
+        (pinned here if it is not); every round copies its samples host->device, runs the one-hop /
+        multi-hop chains and copies the new samples back (a round = one call of chunks_per_call hops, or
+        with chunks_per_call == 1 a pipelined group of up to pipeline_frames() hops).  Returns
+        y [B,S,N] on the host (`out`: a pinned [B,S,>=N] tensor to write into).  Synchronises."""
         dev = embed_dev.device
         self._require_cuda(embed_dev)
         self._sync_weights(dev)
@@ -364,12 +366,21 @@ class Net(nn.Module):
         xh = x_host.contiguous().float()
         if not xh.is_pinned():
             xh = xh.pin_memory()
-        yh = torch.empty(Bsz, self.num_src, n_calls * step, dtype=torch.float32).pin_memory()
+        grp = max(chunks_per_call, self.pipeline_frames() if chunks_per_call == 1 else 1)
+        key = (Bsz, n_calls * step, grp, str(dev))
+        cache = getattr(self, "_host_stage", None)
+        if cache is None or cache[0] != key:        # staging buffers are reused across calls
+            yh_c = torch.empty(Bsz, self.num_src, n_calls * step, dtype=torch.float32).pin_memory()
+            xs = torch.empty(Bsz, self.num_ch, hop * grp + la, dtype=torch.float32, device=dev)
+            ys = torch.empty(Bsz, self.num_src, hop * grp, dtype=torch.float32, device=dev)
+            cache = (key, yh_c, xs, ys)
+            self._host_stage = cache
+        _, yh_c, xs, ys = cache
+        yh = out if out is not None else yh_c
+        if not yh.is_pinned() or yh.shape[-1] < n or not yh.is_contiguous():
+            raise ValueError("out must be a contiguous pinned [B, S, >= N] float32 tensor")
         if state is None:
             state = self.init_buffers(Bsz, dev)
-        grp = max(chunks_per_call, self.pipeline_frames() if chunks_per_call == 1 else 1)
-        xs = torch.empty(Bsz, self.num_ch, hop * grp + la, dtype=torch.float32, device=dev)
-        ys = torch.empty(Bsz, self.num_src, hop * grp, dtype=torch.float32, device=dev)
         ws, _ = self._stream_workspace(dev, Bsz, chunks_per_call)
         emb = embed_dev.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
@@ -378,7 +389,7 @@ class Net(nn.Module):
                 yh.shape[-1], Bsz, n_calls, chunks_per_call, xs.data_ptr(), ys.data_ptr(), ws.data_ptr(),
                 ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         self._last_stream_state = state
-        return yh[..., :n]
+        return yh[..., :n] if out is not None else yh[..., :n].clone()
 
     # ---- debugging aid for the parity tests ------------------------------------------------------
     def forward_with_taps(self, x, embeds):
