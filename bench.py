@@ -208,6 +208,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- weights: rank 0 owns them, NCCL broadcast to the other ranks ---------------------------
@@ -438,22 +440,26 @@ def kernel_algorithmic_bytes(name, cpc):
     return rows * 64 * 4 * 2
 
 
-def profile_chain(net, x_dev, emb, dev, cpc, iters=20):
+def profile_chain(net, x_dev, emb, dev, cpc, iters=20, batch=1):
     """Times every kernel of the chain with CUDA events (l2h_sep_profile) -> {name: {ms_mean, ms_total}}."""
     from lookoncetohear_b200 import _cabi
     L = _cabi.lib()
     net._sync_weights(dev)
-    st = net.init_buffers(1, dev)
-    ws, _ = net._workspace(dev, 1, cpc)
+    st = net.init_buffers(batch, dev)
+    ws, _ = net._workspace(dev, batch, cpc)
     n = ctypes.c_int32()
     names = (ctypes.c_char_p * 64)()
     ms = (ctypes.c_float * 64)()
     cnt = (ctypes.c_int32 * 64)()
-    y = torch.empty(1, 2, HOP * cpc, device=dev)
+    y = torch.empty(batch, 2, HOP * cpc, device=dev)
     x = x_dev[..., :HOP * cpc + 64].contiguous()
+    if x.shape[0] != batch:
+        x = x[:1].expand(batch, -1, -1).contiguous()
+    if emb.shape[0] != batch:
+        emb = emb[:1].expand(batch, -1).contiguous()
     with torch.cuda.device(dev):
         _cabi.check(L.l2h_sep_profile(net._engine(), x.data_ptr(), x.shape[-1], emb.data_ptr(), st.buf.data_ptr(),
-                                      y.data_ptr(), 1, cpc, ws.data_ptr(), ws.numel(), iters, names, ms, cnt,
+                                      y.data_ptr(), batch, cpc, ws.data_ptr(), ws.numel(), iters, names, ms, cnt,
                                       ctypes.byref(n), torch.cuda.current_stream(dev).cuda_stream))
     out = {}
     for i in range(n.value):
