@@ -57,7 +57,7 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
-    cudaStream_t pipe_streams[32] = {};
+    cudaStream_t pipe_streams[40] = {};
     std::vector<cudaEvent_t> pipe_events;
     int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
     int pipe_alanes = 4;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
@@ -410,10 +410,11 @@ constexpr int PIPE_LANES = 4;      // max hops of stage A (BiLSTM) in flight per
 constexpr int PIPE_FLANES = 2;     // front_kernel lanes (frames of a group do not depend on each other there)
 constexpr int PIPE_BLANES = 3;     // back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
-constexpr int PIPE_PER_BLOCK = PIPE_LANES + 4;     // A lanes, B1 (mid), Bq (qkv), Ba (attention), Bo (attn_out)
+constexpr int PIPE_OLANES = 2;     // attn_out lanes (no hop-to-hop dependency)
+constexpr int PIPE_PER_BLOCK = PIPE_LANES + 3 + PIPE_OLANES;     // A lanes, B1 (mid), Bq (qkv), Ba (attention), Bo lanes (attn_out)
 constexpr int PIPE_STREAMS = PIPE_BASE + 3 * PIPE_PER_BLOCK;
 constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites a ring row hop t's attention still reads
-static_assert(PIPE_STREAMS <= 32, "pipe_streams[]");
+static_assert(PIPE_STREAMS <= 40, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
 
@@ -455,9 +456,10 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     auto sB1 = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES]; };
     auto sBq = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1]; };
     auto sBa = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 2]; };
-    auto sB2b = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 3]; };
+    auto sBo = [&](int b, int k) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 3 + k % PIPE_OLANES]; };
     // attention-done events of the last PIPE_QKV_AHEAD+1 hops per block (ring write-after-read guard)
     std::vector<std::vector<cudaEvent_t>> att_done(3, std::vector<cudaEvent_t>(K, nullptr));
+    std::vector<cudaEvent_t> out_done(K, nullptr);      // last block's attn_out of hop k (back(k) also reads hops k-1..k-3)
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
     for (int k = 0; k < K; ++k) {
@@ -501,10 +503,18 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
             }
             if (int rc = next_event(&att_done[b][k])) return rc;
             CK(cudaEventRecord(att_done[b][k], sBa(b)));
-            CK(cudaStreamWaitEvent(sB2b(b), att_done[b][k], 0));
-            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sB2b(b), (const float*)Z, X, (const float*)state, ss,
+            CK(cudaStreamWaitEvent(sBo(b, k), att_done[b][k], 0));
+            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X, (const float*)state, ss,
                         W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
-            if (int rc = edge(sB2b(b), b < 2 ? sA(b + 1, lane) : sBack)) return rc;
+            if (b < 2) {
+                if (int rc = edge(sBo(b, k), sA(b + 1, lane))) return rc;
+            } else {
+                if (int rc = next_event(&out_done[k])) return rc;
+                CK(cudaEventRecord(out_done[k], sBo(b, k)));
+                CK(cudaStreamWaitEvent(sBack, out_done[k], 0));
+                // the previous hop's output sits on the other attn_out lane: wait for it too (k-2, k-3 follow in-lane)
+                if (k >= 1) CK(cudaStreamWaitEvent(sBack, out_done[k - 1], 0));
+            }
         }
         CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state,
                     ss, e->w, 1, a.pos_rel, k, K, k * HOP, slot));
