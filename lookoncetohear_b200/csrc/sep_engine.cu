@@ -212,7 +212,7 @@ static void resolve_pointers(SepEngine* e) {
 
 // ---- workspace carve-up (floats) ---------------------------------------------------------------
 struct Workspace {
-    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, PART, QKVRAW, TAPS, total;
+    int64_t X, GX, Y, Z, Q, KALL, VALL, PRE, QKVRAW, TAPS, total;
 };
 // few frames in flight -> split every head's 50-row window over several CTAs
 static int attn_splits(int B, int T) {
@@ -233,7 +233,6 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.KALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * QK_LD : 0);
     ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
     ws.PRE = alloc((int64_t)B * FC);
-    ws.PART = alloc(0);      // (split-attention partials now live in distributed shared memory)
     ws.QKVRAW = alloc(T == 1 ? (int64_t)B * NF * NQKV : 0);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
     ws.total = cur;
@@ -289,7 +288,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     if (rows > 0x7fffffff / 2) return fail(1, "batch*frames too large for one call; split the batch");
     float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
     float* Q = wsp + ws.Q; float* KALL = wsp + ws.KALL; float* VALL = wsp + ws.VALL; float* PRE = wsp + ws.PRE;
-    float* TAPS = wsp + ws.TAPS; float* PART = wsp + ws.PART;
+    float* TAPS = wsp + ws.TAPS;
     float* QKVRAW = wsp + ws.QKVRAW;
     const int nsplit = attn_splits(B, T);
     // one-frame calls: the row-local middle of every block runs as ONE fused kernel (mid_kernel.cuh).
@@ -377,11 +376,11 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                         (const float*)KALL, (const float*)VALL, Z, T));
         } else {
             CK(launch_k(pdl, attn_kernel, dim3(T, NHEAD, B), dim3(256), 0, st, (const float*)Q, (const float*)KALL,
-                        (const float*)VALL, (const float*)state, ss, b, Z, PART, 1, T, 0));
+                        (const float*)VALL, (const float*)state, ss, b, Z, T, 0));
         }
         MARK("attn");
         CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
-                    (b == 0 && e->n_blocks > 1) ? 1 : 0, (const float*)PART, 1, T));
+                    (b == 0 && e->n_blocks > 1) ? 1 : 0, T));
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
@@ -499,13 +498,13 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                                   (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
             } else {
                 CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sBa(b), (const float*)Q, (const float*)nullptr,
-                            (const float*)nullptr, (const float*)state, ss, b, Z, (float*)nullptr, 1, 1, k));
+                            (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
             }
             if (int rc = next_event(&att_done[b][k])) return rc;
             CK(cudaEventRecord(att_done[b][k], sBa(b)));
             CK(cudaStreamWaitEvent(sBo(b, k), att_done[b][k], 0));
             CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X, (const float*)state, ss,
-                        W, b == 0 ? 1 : 0, (const float*)nullptr, 1, 1));
+                        W, b == 0 ? 1 : 0, 1));
             if (b < 2) {
                 if (int rc = edge(sBo(b, k), sA(b + 1, lane))) return rc;
             } else {

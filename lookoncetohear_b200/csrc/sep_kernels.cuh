@@ -402,33 +402,27 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
 
 // ------------------------------------------------------------------------------------------
 // K4b local attention: each query attends to its own frame + the 49 previous ones, unmasked
-// (tfgridnet_causal.py:564-581).  grid (T, 4*nsplit, B), 256 threads.
-// T == 1: K/V rows are the 50 ring slots (order is irrelevant to softmax-weighted sums);
-// T  > 1: rows t .. t+49 of the linear scratch.
-// nsplit > 1 (few frames in flight): the 50 rows of a head are split over nsplit CTAs, each writing
-// an un-normalised partial (max, sum, o[1552]) that attn_out_kernel merges (flash-decoding style).
-constexpr int PART_LD = V_DIM + 4;      // [o (1552) | m | l | pad pad]
-
+// (tfgridnet_causal.py:564-581).  One CTA per (frame, head, stream): grid (T, 4, B), 256 threads.
+// T == 1: K/V rows are ring slots (frame n lives in slot n mod RING); T > 1: rows t .. t+49 of the
+// linear scratch.  Used when there are enough (frame, head, stream) items to fill the GPU but too few
+// frames per stream to tile (e.g. 256 streams x 1 hop); see attn_cluster_kernel / attn_tile_kernel.
 __global__ void __launch_bounds__(256)
 attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, const float* __restrict__ Vall,
-            const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z,
-            float* __restrict__ part, int nsplit, int T, int frame_k) {
+            const float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Z, int T, int frame_k) {
     __shared__ __align__(16) float qs[QK_LD];
     __shared__ float sc[64];
     griddep_launch();
     griddep_wait();
-    const int t = blockIdx.x, h = blockIdx.y / nsplit, sp = blockIdx.y % nsplit, b = blockIdx.z, tid = threadIdx.x;
-    const int rows_per = (ATT + nsplit - 1) / nsplit;
-    const int j0 = sp * rows_per, j1 = min(ATT, j0 + rows_per), nr = j1 - j0;
+    const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
     const int64_t bh = (int64_t)b * NHEAD + h;
     const float* kb;
     const float* vb;
-    int first = j0, wrap = 0x7fffffff;      // window row j -> storage row (first + j) % wrap
-    if (T == 1) {                           // ring: window = frames pos-49 .. pos, frame n lives in slot n mod RING
+    int first = 0, wrap = 0x7fffffff;       // window row j -> storage row (first + j) % wrap
+    if (T == 1) {                           // ring: window = frames pos-49 .. pos
         const float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
         kb = sb + BK_K + (int64_t)h * RING * QK_LD;
         vb = sb + BK_V + (int64_t)h * RING * V_DIM;
-        const long long p0 = reinterpret_cast<const StateHeader*>(state)->pos + frame_k - (ATT - 1) + j0;
+        const long long p0 = reinterpret_cast<const StateHeader*>(state)->pos + frame_k - (ATT - 1);
         first = (int)(((p0 % RING) + RING) % RING);
         wrap = RING;
     } else {
@@ -441,7 +435,7 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     const float scale = rsqrtf((float)QK_DIM);
-    for (int j = warp; j < nr; j += 8) {
+    for (int j = warp; j < ATT; j += 8) {
         const float4* kr = reinterpret_cast<const float4*>(kb + (int64_t)((first + j) % wrap) * QK_LD);
         float4 kv[5];
 #pragma unroll
@@ -462,52 +456,35 @@ attn_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Kall, cons
         if (lane == 0) sc[j] = s * scale;
     }
     __syncthreads();
-    float mx = -INFINITY, lsum = 0.f;
     if (warp == 0) {
-        const float a0 = (lane < nr) ? sc[lane] : -INFINITY;
-        const float a1 = (lane + 32 < nr) ? sc[lane + 32] : -INFINITY;
-        mx = warp_max(fmaxf(a0, a1));
-        const float e0 = (lane < nr) ? __expf(a0 - mx) : 0.f;
-        const float e1 = (lane + 32 < nr) ? __expf(a1 - mx) : 0.f;
-        lsum = warp_sum(e0 + e1);
-        const float inv = (nsplit == 1) ? 1.f / lsum : 1.f;
-        if (lane < nr) sc[lane] = e0 * inv;
-        if (lane + 32 < nr) sc[lane + 32] = e1 * inv;
+        const float a0 = sc[lane];
+        const float a1 = (lane + 32 < ATT) ? sc[lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(a0, a1));
+        const float e0 = __expf(a0 - mx);
+        const float e1 = (lane + 32 < ATT) ? __expf(a1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        sc[lane] = e0 * inv;
+        if (lane + 32 < ATT) sc[lane + 32] = e1 * inv;
     }
     __syncthreads();
     float* zr = Z + ((int64_t)b * T + t) * NF * CH;
-    float* pr = part + ((((int64_t)b * T + t) * NHEAD + h) * nsplit + sp) * PART_LD;
     for (int c4 = tid; c4 < V_DIM / 4; c4 += 256) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nr <= 5) {                      // split mode: all rows in flight at once
-            float4 v[5];
+        for (int j0 = 0; j0 < ATT; j0 += 10) {       // 10 value rows in flight per thread
+            float4 v[10];
 #pragma unroll
-            for (int j = 0; j < 5; ++j)
-                v[j] = (j < nr) ? reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % wrap) * V_DIM)[c4]
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 10; ++u)
+                v[u] = reinterpret_cast<const float4*>(vb + (int64_t)((first + j0 + u) % wrap) * V_DIM)[c4];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float p = (j < nr) ? sc[j] : 0.f;
-                acc.x = fmaf(p, v[j].x, acc.x); acc.y = fmaf(p, v[j].y, acc.y);
-                acc.z = fmaf(p, v[j].z, acc.z); acc.w = fmaf(p, v[j].w, acc.w);
-            }
-        } else {
-#pragma unroll 10
-            for (int j = 0; j < nr; ++j) {
-                const float4 v = reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % wrap) * V_DIM)[c4];
-                const float p = sc[j];
-                acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
-                acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+            for (int u = 0; u < 10; ++u) {
+                const float p = sc[j0 + u];
+                acc.x = fmaf(p, v[u].x, acc.x); acc.y = fmaf(p, v[u].y, acc.y);
+                acc.z = fmaf(p, v[u].z, acc.z); acc.w = fmaf(p, v[u].w, acc.w);
             }
         }
-        if (nsplit == 1) {
-            const int f = c4 >> 2, c0 = (c4 & 3) * 4;        // feature f*16 + c -> channel h*16 + c
-            *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
-        } else {
-            *reinterpret_cast<float4*>(pr + c4 * 4) = acc;
-        }
+        const int f = c4 >> 2, c0 = (c4 & 3) * 4;            // feature f*16 + c -> channel h*16 + c
+        *reinterpret_cast<float4*>(zr + f * CH + h * VD + c0) = acc;
     }
-    if (nsplit > 1 && tid == 0) { pr[V_DIM] = mx; pr[V_DIM + 1] = lsum; }
 }
 
 // K4b'' query-tiled local attention for multi-frame calls: consecutive queries share 49 of their 50
@@ -743,10 +720,9 @@ constexpr size_t AOUT_SMEM = (size_t)(64 * 100 + 64 * 64 + NF * 64 + 4 * FC) * s
 
 __global__ void __launch_bounds__(256)
 attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float* __restrict__ state,
-                int64_t sstride, BlockWeights w, int apply_gate, const float* __restrict__ part, int nsplit, int T) {
+                int64_t sstride, BlockWeights w, int apply_gate, int T) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
-    __shared__ float coef[NHEAD][16];
     float* Zt = sm;                 // [64][100]
     float* Ws = Zt + 64 * 100;      // [64][64]
     float* P = Ws + 64 * 64;        // [97][64]
@@ -773,47 +749,13 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     __syncthreads();
     tma_load_split(Xr, xr, FC * 4, &bars[1], tid, 256);
     if (apply_gate) tma_load_split(Gt, gate, FC * 4, &bars[1], tid, 256);
-    if (nsplit == 1) {
+    {
         const float* zr = Z + ((int64_t)b * T + t) * NF * CH;
         for (int i = tid; i < 100 * 16; i += 256) {
             const int c4 = i / 100, f = i % 100;
             const float4 v = (f < NF) ? *reinterpret_cast<const float4*>(zr + f * CH + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             Zt[(c4 * 4 + 0) * 100 + f] = v.x; Zt[(c4 * 4 + 1) * 100 + f] = v.y;
             Zt[(c4 * 4 + 2) * 100 + f] = v.z; Zt[(c4 * 4 + 3) * 100 + f] = v.w;
-        }
-    } else {                                   // merge the split-attention partials
-        const float* pb = part + ((int64_t)b * T + t) * NHEAD * nsplit * PART_LD;
-        if (tid < NHEAD) {
-            float mstar = -INFINITY;
-            for (int s2 = 0; s2 < nsplit; ++s2) mstar = fmaxf(mstar, pb[(tid * nsplit + s2) * PART_LD + V_DIM]);
-            float den = 0.f;
-            for (int s2 = 0; s2 < nsplit; ++s2) {
-                const float wgt = __expf(pb[(tid * nsplit + s2) * PART_LD + V_DIM] - mstar);
-                coef[tid][s2] = wgt;
-                den += wgt * pb[(tid * nsplit + s2) * PART_LD + V_DIM + 1];
-            }
-            const float inv = 1.f / den;
-            for (int s2 = 0; s2 < nsplit; ++s2) coef[tid][s2] *= inv;
-        }
-        __syncthreads();
-        for (int i = tid; i < 3 * 64; i += 256) Zt[(i % 64) * 100 + NF + i / 64] = 0.f;     // pad rows 97..99
-        for (int i = tid; i < NF * NHEAD * 4; i += 256) {       // item = (f, head, 4 channels)
-            const int c4 = i & 3, hh = (i >> 2) & 3, f = i >> 4;
-            float4 v[10];
-#pragma unroll
-            for (int s2 = 0; s2 < 10; ++s2)
-                v[s2] = (s2 < nsplit) ? *reinterpret_cast<const float4*>(pb + (hh * nsplit + s2) * PART_LD + f * VD + c4 * 4)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int s2 = 0; s2 < 10; ++s2) {
-                const float cf = (s2 < nsplit) ? coef[hh][s2] : 0.f;
-                o.x = fmaf(cf, v[s2].x, o.x); o.y = fmaf(cf, v[s2].y, o.y);
-                o.z = fmaf(cf, v[s2].z, o.z); o.w = fmaf(cf, v[s2].w, o.w);
-            }
-            const int k = hh * VD + c4 * 4;
-            Zt[(k + 0) * 100 + f] = o.x; Zt[(k + 1) * 100 + f] = o.y;
-            Zt[(k + 2) * 100 + f] = o.z; Zt[(k + 3) * 100 + f] = o.w;
         }
     }
     mbar_wait(&bars[0], 0);
