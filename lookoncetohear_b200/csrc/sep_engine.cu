@@ -370,7 +370,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
                               (const float*)Q, (const float*)KALL, (const float*)VALL, (const float*)state, ss, b, Z, T, 0));
-        } else if ((int64_t)B * NHEAD * ((T + ATT_TQ - 1) / ATT_TQ) >= 148) {   // enough tiles to fill the GPU: query-tiled,
+        } else if (T > 1 && (int64_t)B * NHEAD * ((T + ATT_TQ - 1) / ATT_TQ) >= 148) {   // enough tiles to fill the GPU: query-tiled,
             // one pass over 57 rows serves 8 queries
             CK(launch_k(pdl, attn_tile_kernel, dim3((T + ATT_TQ - 1) / ATT_TQ, NHEAD, B), dim3(256), 0, st, (const float*)Q,
                         (const float*)KALL, (const float*)VALL, Z, T));

@@ -61,6 +61,12 @@ def test_batched_streaming_many_streams(sep, dev):
         y_stream = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
         y_whole = net(xd, e.to(dev)).cpu()
     assert rs.rel_l2(y_stream, y_whole) < 1e-4
+    # the same through the reference-shaped API: one predict() call per hop for all 256 streams
+    st = net.init_buffers(B, dev)
+    xp = F.pad(xd, (0, 64))
+    with torch.no_grad():
+        y_pred = torch.cat([net.predict(xp[..., 128 * i:128 * i + 192], ed, st, pad=False)[0] for i in range(8)], -1).cpu()
+    assert rs.rel_l2(y_pred, y_whole[..., :128 * 8]) < 1e-4
     for b in (0, 101, 255):
         y_ref = rs.sep_forward(sd, x[b:b + 1], e[b:b + 1])
         assert rs.rel_l2(y_stream[b:b + 1], y_ref) <= 1e-3
