@@ -461,6 +461,175 @@ lstm_rec3_kernel(const LstmArgs a) {
     }
 }
 
+// ---- variant 4: variant 3's thread layout, throughput mode --------------------------------------
+// With many sequences per CTA, variant 3 measured ~410 ns per (sequence, step) however many sequences the
+// CTA holds (profiles/r01e_kernel_us_batch256.jsonl: 855 ns/step at NSEQ = 2): 214-226 registers leave the
+// scheduler no room to overlap the sequences' dependent chains.  Here the step is written stage by stage
+// ACROSS the CTA's sequences (all dot products, then all reductions, then all activations) with one
+// accumulator pair per gate, so NSEQ independent chains are in flight at every stage.
+template <int NSEQ>
+__global__ void __launch_bounds__(128, 2)
+lstm_rec4_kernel(const LstmArgs a) {
+    __shared__ __align__(16) float hbuf[2][NSEQ][64];
+    __shared__ __align__(16) float gring[L3_STAGES][NSEQ][256];
+
+    griddep_launch();
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const int seq0 = blockIdx.x * NSEQ;
+    const int j = tid >> 1, kh = tid & 1;
+
+    float2 w[4][16];                      // rows j*4+q, k in [32 kh, 32 kh + 32)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4* wp = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + j * 4 + q) * 64 + 32 * kh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 t = __ldg(wp + k);
+            w[q][2 * k] = make_float2(t.x, t.y);
+            w[q][2 * k + 1] = make_float2(t.z, t.w);
+        }
+    }
+    griddep_wait();
+
+    const bool own_out = (a.out_outer_stride | a.out_inner_stride | a.out_step_stride) != 0;
+    const int64_t o_step = (own_out ? a.out_step_stride : a.step_stride) * a.out_ld;
+    const int sgn = (dir == 0) ? 1 : -1;
+    const int first = (dir == 0) ? 0 : a.L - 1;
+    const int64_t g_step = a.step_stride * a.gx_ld * sgn;
+
+    float c[NSEQ];
+    bool valid[NSEQ];
+    float* outp[NSEQ];
+    int64_t hc[NSEQ];
+    const float* grow[NSEQ];
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) {
+        const int seq = seq0 + s;
+        valid[s] = seq < a.nseq;
+        const int sq = valid[s] ? seq : 0;
+        const int so = sq / a.inner_count, si = sq % a.inner_count;
+        const int64_t gb = (int64_t)so * a.outer_stride + (int64_t)si * a.inner_stride;
+        const int64_t ob = own_out ? (int64_t)so * a.out_outer_stride + (int64_t)si * a.out_inner_stride : gb;
+        grow[s] = a.gx + (gb + (int64_t)first * a.step_stride) * a.gx_ld + dir * 256;
+        outp[s] = a.out + ob * a.out_ld + (int64_t)first * o_step + dir * 64 + j;
+        hc[s] = (int64_t)so * a.hc_outer_stride + (int64_t)si * 64 + j;
+        c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
+        if (kh == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
+    }
+    auto issue_group = [&](int g) {       // rows 4g .. 4g+3 -> stages (g % 2)*4 .. +3 ; 64 x 16 B chunks per row
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int idx = tid + 128 * u, r = idx >> 6, chunk = idx & 63;
+                const int it = 4 * g + r;
+                if (valid[s] && it < a.L)
+                    cp_async16(&gring[(g % 2) * 4 + r][s][chunk * 4], grow[s] + (int64_t)it * g_step + chunk * 4);
+            }
+        }
+        cp_async_commit();
+    };
+    issue_group(0);
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const float LOG2E = 1.4426950408889634f;
+    const float S0 = kh ? -2.f * LOG2E : -LOG2E, A0 = kh ? 2.f : 1.f, B0 = kh ? -1.f : 0.f;
+
+    int cur = 0;
+    for (int it = 0; it < a.L; ++it) {
+        if ((it & 3) == 0) issue_group((it >> 2) + 1);              // overwrites the group consumed 4 steps ago
+        // stage A: all dot products (4 NSEQ independent FFMA2 chains)
+        float2 acc[NSEQ][4];
+        float2 g2[NSEQ];
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            g2[s] = *reinterpret_cast<const float2*>(&gring[it % L3_STAGES][s][j * 4 + 2 * kh]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[s][q] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float4 h4[NSEQ];
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s) h4[s] = *reinterpret_cast<const float4*>(&hbuf[cur][s][32 * kh + 4 * k]);
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s) {
+                const float2 hA = make_float2(h4[s].x, h4[s].y);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[s][q] = ffma2(w[q][2 * k], hA, acc[s][q]);
+            }
+#pragma unroll
+            for (int s = 0; s < NSEQ; ++s) {
+                const float2 hB = make_float2(h4[s].z, h4[s].w);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[s][q] = ffma2(w[q][2 * k + 1], hB, acc[s][q]);
+            }
+        }
+        // stage B: k-half reduction; lane kh adds gx of gates 2kh, 2kh+1
+        float p[NSEQ][4];
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float gadd = ((q >> 1) == kh) ? ((q & 1) ? g2[s].y : g2[s].x) : 0.f;
+                p[s][q] = (acc[s][q].x + acc[s][q].y) + gadd;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p[s][q] += __shfl_xor_sync(0xffffffffu, p[s][q], 1);
+        }
+        // stage C: lane kh = 0 activates (i, f); lane kh = 1 activates (g, o)
+        float v0[NSEQ], v1[NSEQ], e0[NSEQ], e1[NSEQ];
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            e0[s] = ex2_ftz(S0 * (kh ? p[s][2] : p[s][0]));
+            e1[s] = ex2_ftz(-LOG2E * (kh ? p[s][3] : p[s][1]));
+        }
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            v0[s] = __fdividef(A0, 1.f + e0[s]) + B0;
+            v1[s] = __fdividef(1.f, 1.f + e1[s]);
+        }
+        float og[NSEQ], oo[NSEQ];
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            og[s] = __shfl_xor_sync(0xffffffffu, v0[s], 1);
+            oo[s] = __shfl_xor_sync(0xffffffffu, v1[s], 1);
+        }
+        float ec[NSEQ];
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            c[s] = v1[s] * c[s] + v0[s] * og[s];        // meaningful on kh == 0 lanes: f*c + i*g
+            ec[s] = ex2_ftz(-2.f * LOG2E * c[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            const float h = oo[s] * (__fdividef(2.f, 1.f + ec[s]) - 1.f);
+            if (kh == 0) {
+                hbuf[cur ^ 1][s][j] = h;
+                if (valid[s]) *outp[s] = h;
+            }
+            outp[s] += sgn * o_step;
+        }
+        cur ^= 1;
+        if ((it & 3) == 3) cp_async_wait<0>();          // the next four rows (issued 4 steps ago) have landed
+        __syncthreads();
+    }
+    if (a.h_state != nullptr) {
+#pragma unroll
+        for (int s = 0; s < NSEQ; ++s) {
+            if (valid[s] && kh == 0) {
+                a.h_state[hc[s]] = hbuf[cur][s][j];
+                a.c_state[hc[s]] = c[s];
+            }
+        }
+    }
+}
+
 inline int lstm_variant() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("L2H_LSTM_V"); v = e ? atoi(e) : 3; }
@@ -481,7 +650,12 @@ inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st, bool pdl 
         }
         int per = 1;
         while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
+        static const int force_per = [] { const char* e = getenv("L2H_LSTM_PER"); return e ? atoi(e) : 0; }();
+        static const bool staged = [] { const char* e = getenv("L2H_LSTM_STAGED"); return e ? atoi(e) != 0 : true; }();
+        if (force_per == 1 || force_per == 2 || force_per == 4) per = force_per;
         dim3 grid((a.nseq + per - 1) / per, a.ndir);
+        if (staged && per == 2) return launch_k(pdl, lstm_rec4_kernel<2>, grid, dim3(128), 0, st, a);
+        if (staged && per == 4) return launch_k(pdl, lstm_rec4_kernel<4>, grid, dim3(128), 0, st, a);
         switch (per) {
             case 1: return launch_k(pdl, lstm_rec3_kernel<1, false>, grid, dim3(128), 0, st, a);
             case 2: return launch_k(pdl, lstm_rec3_kernel<2, false>, grid, dim3(128), 0, st, a);

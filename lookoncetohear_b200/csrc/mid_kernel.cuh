@@ -5,9 +5,20 @@
 //     X2 = X1 + h' W_l2^T + b                     inter Linear(64->64) + residual      (:534-538)
 //     P  = PReLU(X2 W_qkv^T + b)                  the three attention projections      (:547-551, :354-387)
 // The generic chain runs this as four row-GEMMs + one recurrence launch + the GEMM half of
-// qkv_kernel.  Here one CTA keeps all five weight matrices (204 KB) in shared memory -- loaded
-// BEFORE griddepcontrol.wait, i.e. while the 97-step intra recurrence is still running -- and
-// pushes a tile of RT rows through the whole section.  grid (ceil(97/RT), B), 256 threads.
+// qkv_kernel.  Here one CTA keeps all the weight matrices (205 KB, one packed buffer) in shared memory --
+// loaded BEFORE griddepcontrol.wait, i.e. while the 97-step intra recurrence is still running -- and
+// pushes tiles of 8 rows through the whole section.  Persistent: grid = min(#tiles, #SMs) CTAs, each
+// loading the weights ONCE and looping over (stream, row-tile) items.
+//
+// Tiling (v2).  With only 8 rows per tile the activations are the broadcast operand, and a broadcast
+// LDS costs one shared-memory wavefront per 4 B per lane whatever its width (profiles/r01c_lstm_microbench.txt),
+// so a warp computing R rows x C columns per lane gets 32 R C / (R + C) FMAs per wavefront: v1 (C = 1,
+// R = 2 or 8) was bound by the shared-memory pipe at 12 k wavefronts and 9.7 us per tile (ncu,
+// profiles/r01e_ncu_batch256.md).  v2 splits K across KQ adjacent lanes instead of giving every lane its own
+// column: a lane accumulates 8 rows x C = 4 or 8 columns over K/KQ values of k, the KQ partial tiles are
+// summed by a shuffle reduce-scatter, and every lane ends up owning 8 C / KQ finished outputs for the
+// epilogue.  Weights and activations are stored in k-slices padded by 4 floats so that the 8 lanes of a
+// quarter-warp (one LDS.128 phase) hit 32 distinct banks.
 #pragma once
 #include "common.cuh"
 #include "sep_kernels.cuh"
@@ -15,161 +26,404 @@
 namespace l2h {
 
 constexpr int MID_RT = 8;
-constexpr size_t MID_SMEM = (size_t)(128 * 64 + 64 * 256 + 64 * 256 + 64 * 64 + 64 * NQKV   // weights
-                                     + 128 * MID_RT + 4 * 64 * MID_RT + 256 * MID_RT) * sizeof(float);
+// phase geometry: K, N, C (columns per lane), KQ (k-slices = lanes per column group), KS = K / KQ
+constexpr int M1_K = 128, M1_N = 64, M1_C = 4, M1_KQ = 16, M1_KS = 8;        // intra linear
+constexpr int M3_K = 64, M3_N = 256, M3_C = 8, M3_KQ = 8, M3_KS = 8;         // LN(X1) x W_ih and h x W_hh (two products)
+constexpr int M5_K = 64, M5_N = 64, M5_C = 4, M5_KQ = 16, M5_KS = 4;         // inter linear
+constexpr int M6_K = 64, M6_N = NQKV, M6_C = 4, M6_KQ = 8, M6_KS = 8;        // q|k|v projections
+__host__ __device__ constexpr int mid_wslice(int ks, int n) { return ks * n + 4; }
+__host__ __device__ constexpr int mid_aslice(int ks) { return ks * MID_RT + 4; }
+// BlockWeights::mid_pack: the five matrices k-sliced, in the order the split kernels need them contiguous
+constexpr int MID_W1 = 0;
+constexpr int MID_W3A = MID_W1 + M1_KQ * mid_wslice(M1_KS, M1_N);            // W_ih
+constexpr int MID_W3B = MID_W3A + M3_KQ * mid_wslice(M3_KS, M3_N);           // W_hh
+constexpr int MID_W5 = MID_W3B + M3_KQ * mid_wslice(M3_KS, M3_N);
+constexpr int MID_W6 = MID_W5 + M5_KQ * mid_wslice(M5_KS, M5_N);
+constexpr int MID_PACK = MID_W6 + M6_KQ * mid_wslice(M6_KS, M6_N);           // floats in BlockWeights::mid_pack
+constexpr int MID_A1 = M1_KQ * mid_aslice(M1_KS), MID_A3 = M3_KQ * mid_aslice(M3_KS);
+constexpr int MID_A5 = M5_KQ * mid_aslice(M5_KS), MID_A6 = M6_KQ * mid_aslice(M6_KS);
+constexpr size_t MID_SMEM = (size_t)(MID_PACK + MID_A1 + 2 * MID_A3 + MID_A5 + MID_A6 + MID_RT * 64) * sizeof(float);
+constexpr size_t MID_A_SMEM = (size_t)((MID_W3B - MID_W1) + MID_A1 + MID_A3 + MID_RT * 64) * sizeof(float);
+constexpr size_t MID_B_SMEM = (size_t)((MID_W5 - MID_W3B) + MID_A3) * sizeof(float);
+constexpr size_t MID_C_SMEM = (size_t)((MID_PACK - MID_W5) + MID_A5 + MID_A6) * sizeof(float);
+static_assert(MID_SMEM <= 227 * 1024, "mid_kernel shared memory");
+static_assert((MID_W3A % 4) == 0 && (MID_W3B % 4) == 0 && (MID_W5 % 4) == 0 && (MID_W6 % 4) == 0 && (MID_PACK % 4) == 0, "16-byte slices");
+
+// index of activation (k, row r) in a k-sliced tile
+__host__ __device__ constexpr int mid_aidx(int ks, int k, int r) { return (k / ks) * (ks * MID_RT + 4) + (k % ks) * MID_RT + r; }
+// index of weight (k, n) in a k-sliced [K][N] matrix
+__host__ __device__ constexpr int mid_widx(int ks, int n_cols, int k, int n) { return (k / ks) * (ks * n_cols + 4) + (k % ks) * n_cols + n; }
+
+// sum v[] over the KQ adjacent lanes of a group; lane kq keeps the kq-th chunk of NV / KQ values in v[0 ..)
+template <int HALF, int BIT, int NV>
+__device__ __forceinline__ void lane_rs_stage(float (&v)[NV], int kq) {
+    if constexpr (BIT >= 1) {
+        const bool upper = (kq & BIT) != 0;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            const float send = upper ? v[i] : v[i + HALF];
+            const float keep = upper ? v[i + HALF] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+        }
+        lane_rs_stage<HALF / 2, BIT / 2, NV>(v, kq);
+    }
+}
+template <int NV, int KQ>
+__device__ __forceinline__ void lane_reduce_scatter(float (&v)[NV], int kq) {
+    lane_rs_stage<NV / 2, KQ / 2, NV>(v, kq);
+}
+
+// partial products of one lane: 8 rows x C columns over its k-slice, then the group reduce-scatter.
+// Values are ordered row-major (v = r * C + c), so lane kq ends with rows/columns [kq * 8C/KQ, ...).
+template <int C, int KQ, int KS, int N>
+__device__ __forceinline__ void mid_mm(const float* __restrict__ Wp, const float* __restrict__ Ap, int cg, int kq,
+                                       float (&v)[MID_RT * C]) {
+    float2 acc[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[c][p] = make_float2(0.f, 0.f);
+    const float* wp = Wp + kq * mid_wslice(KS, N) + cg * C;
+    const float* ap = Ap + kq * mid_aslice(KS);
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * MID_RT);
+        const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * MID_RT + 4);
+        const float2 ar[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+        float wv[C];
+#pragma unroll
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 t = *reinterpret_cast<const float4*>(wp + kk * N + c4 * 4);
+            wv[c4 * 4] = t.x; wv[c4 * 4 + 1] = t.y; wv[c4 * 4 + 2] = t.z; wv[c4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float2 ww = make_float2(wv[c], wv[c]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[c][p] = ffma2(ww, ar[p], acc[c][p]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MID_RT; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[r * C + c] = (r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x;
+    lane_reduce_scatter<MID_RT * C, KQ>(v, kq);
+}
 
 __global__ void __launch_bounds__(256)
 mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ QKV, float* __restrict__ state,
-           int64_t sstride, int blk, BlockWeights w) {
+           int64_t sstride, int blk, BlockWeights w, int n_streams) {
     extern __shared__ __align__(16) float sm[];
-    float* W1 = sm;                       // [128][64]   intra linear, k-major
-    float* W2 = W1 + 128 * 64;            // [64][256]   inter W_ih, k-major, gate cols j*4+q
-    float* W3 = W2 + 64 * 256;            // [64][256]   inter W_hh, k-major
-    float* W4 = W3 + 64 * 256;            // [64][64]    inter linear
-    float* W5 = W4 + 64 * 64;             // [64][112]   q|k|v projections
-    float* yT = W5 + 64 * NQKV;           // [128][RT]   intra LSTM outputs, k-major
-    float* x1 = yT + 128 * MID_RT;        // [RT][64]
-    float* aT = x1 + 64 * MID_RT;         // [64][RT]    LN(X1), k-major
-    float* hT = aT + 64 * MID_RT;         // [64][RT]    h (old, then new), k-major
-    float* x2T = hT + 64 * MID_RT;        // [64][RT]    X2, k-major
-    float* gt = x2T + 64 * MID_RT;        // [RT][256]   gate pre-activations
+    float* Wp = sm;                       // the packed weights (BlockWeights::mid_pack)
+    float* A1 = Wp + MID_PACK;            // intra LSTM outputs Y, k-sliced for phase 1
+    float* A3 = A1 + MID_A1;              // LN(X1), k-sliced for phase 3
+    float* A3h = A3 + MID_A3;             // h, k-sliced for phase 3
+    float* A5 = A3h + MID_A3;             // h', k-sliced for phase 5
+    float* A6 = A5 + MID_A5;              // X2, k-sliced for phase 6
+    float* x1s = A6 + MID_A6;             // [RT][64] X1 (LayerNorm input)
 
     __shared__ __align__(8) unsigned long long wbar;
     griddep_launch();
-    const int tid = threadIdx.x, b = blockIdx.y;
-    const int r0 = blockIdx.x * MID_RT;
-    const int nr = min(MID_RT, NF - r0);
-    // ---- weights -> smem: five TMA bulk copies (independent of the chain, so issued before the wait)
-    if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
+    const int tid = threadIdx.x;
+    constexpr int TILES = (NF + MID_RT - 1) / MID_RT;       // row tiles per stream
+    // ---- weights -> smem: TMA bulk copies (independent of the chain, so issued before the wait) ------
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&wbar, MID_PACK * 4);
+        tma_load_1d(Wp + MID_W1, w.mid_pack + MID_W1, (MID_W3B - MID_W1) * 4, &wbar);
+        tma_load_1d(Wp + MID_W3B, w.mid_pack + MID_W3B, (MID_W5 - MID_W3B) * 4, &wbar);
+        tma_load_1d(Wp + MID_W5, w.mid_pack + MID_W5, (MID_PACK - MID_W5) * 4, &wbar);
+    }
     __syncthreads();
-    if (tid == 0) mbar_expect_tx(&wbar, (128 * 64 + 64 * 256 + 64 * 256 + 64 * 64 + 64 * NQKV) * 4);
-    __syncthreads();
-    tma_load_split(W1, w.wl1_t, 128 * 64 * 4, &wbar, tid, 256);
-    tma_load_split(W2, w.wih2_t, 64 * 256 * 4, &wbar, tid, 256);
-    tma_load_split(W3, w.whh2_t, 64 * 256 * 4, &wbar, tid, 256);
-    tma_load_split(W4, w.wl2_t, 64 * 64 * 4, &wbar, tid, 256);
-    tma_load_split(W5, w.wqkv_t, 64 * NQKV * 4, &wbar, tid, 256);
     griddep_wait();
-    float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-    float* hst = sb + BK_H;
-    float* cst = sb + BK_C;
-    const int64_t row0 = (int64_t)b * NF + r0;
-    // ---- tile loads: Y -> yT (k-major), h -> hT ------------------------------------------------
-    for (int i = tid; i < MID_RT * 32; i += 256) {           // float4 over 128 k
-        const int r = i / 32, k4 = i % 32;
-        const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Y + (row0 + r) * 128 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        yT[(k4 * 4 + 0) * MID_RT + r] = v.x; yT[(k4 * 4 + 1) * MID_RT + r] = v.y;
-        yT[(k4 * 4 + 2) * MID_RT + r] = v.z; yT[(k4 * 4 + 3) * MID_RT + r] = v.w;
-    }
-    for (int i = tid; i < MID_RT * 16; i += 256) {
-        const int r = i / 16, k4 = i % 16;
-        const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        hT[(k4 * 4 + 0) * MID_RT + r] = v.x; hT[(k4 * 4 + 1) * MID_RT + r] = v.y;
-        hT[(k4 * 4 + 2) * MID_RT + r] = v.z; hT[(k4 * 4 + 3) * MID_RT + r] = v.w;
-    }
-    mbar_wait(&wbar, 0);
-    __syncthreads();
-    const int c = tid & 63, rp = tid >> 6;                  // column c, row pair (2rp, 2rp+1)
-    // ---- phase 1: X1 = X + Y W1 + b -----------------------------------------------------------
-    {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 8
-        for (int k = 0; k < 128; ++k) {
-            const float wv = W1[k * 64 + c];
-            const float2 yv = *reinterpret_cast<const float2*>(yT + k * MID_RT + rp * 2);
-            acc = ffma2(make_float2(wv, wv), yv, acc);
+    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
+        const int b = item / TILES;
+        const int r0 = (item % TILES) * MID_RT;
+        const int nr = min(MID_RT, NF - r0);
+        __syncthreads();                    // the previous item's tiles are fully consumed
+        float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+        float* hst = sb + BK_H;
+        float* cst = sb + BK_C;
+        const int64_t row0 = (int64_t)b * NF + r0;
+        // ---- tile loads: Y -> A1, h -> A3h ------------------------------------------------------------
+        {
+            const int r = tid >> 5, k4 = tid & 31;
+            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Y + (row0 + r) * 128 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            A1[mid_aidx(M1_KS, k4 * 4 + 0, r)] = v.x; A1[mid_aidx(M1_KS, k4 * 4 + 1, r)] = v.y;
+            A1[mid_aidx(M1_KS, k4 * 4 + 2, r)] = v.z; A1[mid_aidx(M1_KS, k4 * 4 + 3, r)] = v.w;
         }
-        const float bias = __ldg(w.bl1 + c);
-        const float xa = (rp * 2 < nr) ? X[(row0 + rp * 2) * 64 + c] : 0.f;
-        const float xb = (rp * 2 + 1 < nr) ? X[(row0 + rp * 2 + 1) * 64 + c] : 0.f;
-        x1[(rp * 2) * 64 + c] = xa + acc.x + bias;
-        x1[(rp * 2 + 1) * 64 + c] = xb + acc.y + bias;
+        if (tid < 128) {
+            const int r = tid >> 4, k4 = tid & 15;
+            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            A3h[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; A3h[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
+            A3h[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; A3h[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
+        }
+        mbar_wait(&wbar, 0);
+        __syncthreads();
+        // ---- phase 1: X1 = X + Y W1 + b ;  lane (cg, kq) finishes row kq/2, columns cg*4 + (kq&1)*2 + {0,1}
+        float2 x1v;
+        const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
+        {
+            float v[MID_RT * M1_C];
+            mid_mm<M1_C, M1_KQ, M1_KS, M1_N>(Wp + MID_W1, A1, tid >> 4, tid & 15, v);
+            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl1 + n1));
+            const float2 xo = (r1 < nr) ? *reinterpret_cast<const float2*>(X + (row0 + r1) * 64 + n1) : make_float2(0.f, 0.f);
+            x1v = make_float2(xo.x + v[0] + bias.x, xo.y + v[1] + bias.y);
+            *reinterpret_cast<float2*>(x1s + r1 * 64 + n1) = x1v;
+        }
+        __syncthreads();
+        // ---- phase 2: LayerNorm over channels, one warp per row -> A3 ------------------------------------
+        {
+            const int r = tid >> 5, lane = tid & 31;
+            const float v0 = x1s[r * 64 + lane], v1 = x1s[r * 64 + lane + 32];
+            const float mu = warp_sum(v0 + v1) * (1.f / 64.f);
+            const float d0 = v0 - mu, d1 = v1 - mu;
+            const float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+            A3[mid_aidx(M3_KS, lane, r)] = d0 * rs * __ldg(w.ln2_g + lane) + __ldg(w.ln2_b + lane);
+            A3[mid_aidx(M3_KS, lane + 32, r)] = d1 * rs * __ldg(w.ln2_g + lane + 32) + __ldg(w.ln2_b + lane + 32);
+        }
+        __syncthreads();
+        // ---- phase 3 + 4: gates and LSTM cell; lane (jp, kq) finishes row kq, hidden units 2jp, 2jp+1 ----
+        {
+            // two K = 64 products, combined as (x W_ih + b) + h W_hh: the arithmetic of mid_a_kernel + mid_b_kernel
+            float u[MID_RT * M3_C], v[MID_RT * M3_C];
+            const int jp = tid >> 3, r = tid & 7;
+            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3A, A3, jp, r, u);
+            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3B, A3h, jp, r, v);
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8 + 4));
+            const float4 ga = make_float4(u[0] + ba.x, u[1] + ba.y, u[2] + ba.z, u[3] + ba.w);
+            const float4 gb = make_float4(u[4] + bb.x, u[5] + bb.y, u[6] + bb.z, u[7] + bb.w);
+            const float2 cold = (r < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + r) * 64 + jp * 2) : make_float2(0.f, 0.f);
+            const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
+            const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
+            const float c0 = gf0 * cold.x + gi0 * gg0, c1 = gf1 * cold.y + gi1 * gg1;
+            const float h0 = go0 * fast_tanh(c0), h1 = go1 * fast_tanh(c1);
+            if (r < nr) {
+                *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = make_float2(c0, c1);
+                *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = make_float2(h0, h1);
+            }
+            A5[mid_aidx(M5_KS, jp * 2, r)] = h0;
+            A5[mid_aidx(M5_KS, jp * 2 + 1, r)] = h1;
+        }
+        __syncthreads();
+        // ---- phase 5: X2 = X1 + h' W_l2 + b ; same lane -> output mapping as phase 1 -------------------
+        {
+            float v[MID_RT * M5_C];
+            mid_mm<M5_C, M5_KQ, M5_KS, M5_N>(Wp + MID_W5, A5, tid >> 4, tid & 15, v);
+            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl2 + n1));
+            const float2 x2v = make_float2(x1v.x + v[0] + bias.x, x1v.y + v[1] + bias.y);
+            if (r1 < nr) *reinterpret_cast<float2*>(X + (row0 + r1) * 64 + n1) = x2v;
+            A6[mid_aidx(M6_KS, n1, r1)] = x2v.x;
+            A6[mid_aidx(M6_KS, n1 + 1, r1)] = x2v.y;
+        }
+        __syncthreads();
+        // ---- phase 6: P = PReLU(X2 W_qkv + b); lane (cg < 28, kq) finishes row kq, columns cg*4 .. +3 ----
+        if (tid < (M6_N / M6_C) * M6_KQ) {
+            float v[MID_RT * M6_C];
+            const int cg = tid >> 3, r = tid & 7;
+            mid_mm<M6_C, M6_KQ, M6_KS, M6_N>(Wp + MID_W6, A6, cg, r, v);
+            const float4 bias = __ldg(reinterpret_cast<const float4*>(w.bqkv + cg * 4));
+            const float slope = __ldg(w.slopes + (cg < 6 ? 0 : (cg < 12 ? 1 : 2)));
+            if (r < nr)
+                *reinterpret_cast<float4*>(QKV + (row0 + r) * NQKV + cg * 4) =
+                    make_float4(prelu(v[0] + bias.x, slope), prelu(v[1] + bias.y, slope), prelu(v[2] + bias.z, slope),
+                                prelu(v[3] + bias.w, slope));
+        }
+    }
+}
+
+// ---- the same section as three kernels (wavefront-pipelined one-hop streams, sep_engine.cu) ----------
+// Only the W_hh product and the cell carry state from hop to hop; in the pipeline that part is the stage every
+// hop of a block has to pass through one after the other, so it is kept as small as possible:
+//   mid_a  X1 = X + Y W_l1 + b ; GI = LN(X1) W_ih + b        no carried state: runs on the BiLSTM lanes
+//   mid_b  g = GI + h W_hh ; (h, c) cell ; H' = h'            the serial stage: 64 KB of weights, K = 64
+//   mid_c  X2 = X1 + H' W_l2 + b ; P = PReLU(X2 W_qkv + b)   no carried state: runs on the qkv lanes
+__global__ void __launch_bounds__(256)
+mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ GI, BlockWeights w, int n_streams) {
+    extern __shared__ __align__(16) float sm[];
+    float* W1 = sm;                                   // intra linear, k-sliced
+    float* W3a = W1 + (MID_W3A - MID_W1);             // W_ih, k-sliced
+    float* A1 = W1 + (MID_W3B - MID_W1);
+    float* A3 = A1 + MID_A1;                          // LN(X1), k-sliced
+    float* x1s = A3 + MID_A3;
+    __shared__ __align__(8) unsigned long long wbar;
+    griddep_launch();
+    const int tid = threadIdx.x;
+    constexpr int TILES = (NF + MID_RT - 1) / MID_RT;
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&wbar, (MID_W3B - MID_W1) * 4);
+        tma_load_1d(W1, w.mid_pack + MID_W1, (MID_W3B - MID_W1) * 4, &wbar);
     }
     __syncthreads();
-    // ---- phase 2: LayerNorm over channels, one warp per row -> aT --------------------------------
-    {
-        const int r = tid >> 5, lane = tid & 31;
-        const float v0 = x1[r * 64 + lane], v1 = x1[r * 64 + lane + 32];
-        const float mu = warp_sum(v0 + v1) * (1.f / 64.f);
-        const float d0 = v0 - mu, d1 = v1 - mu;
-        const float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
-        aT[lane * MID_RT + r] = d0 * rs * __ldg(w.ln2_g + lane) + __ldg(w.ln2_b + lane);
-        aT[(lane + 32) * MID_RT + r] = d1 * rs * __ldg(w.ln2_g + lane + 32) + __ldg(w.ln2_b + lane + 32);
-    }
-    __syncthreads();
-    // ---- phase 3: gate pre-activations, thread = gate column, all RT rows --------------------------
-    {
-        float2 acc[MID_RT / 2];
-        const float bias = __ldg(w.b2 + tid);
-#pragma unroll
-        for (int i = 0; i < MID_RT / 2; ++i) acc[i] = make_float2(bias, bias);
-#pragma unroll 4
-        for (int k = 0; k < 64; ++k) {
-            const float w2 = W2[k * 256 + tid], w3 = W3[k * 256 + tid];
-            const float2 ww2 = make_float2(w2, w2), ww3 = make_float2(w3, w3);
-            const float4 a0 = *reinterpret_cast<const float4*>(aT + k * MID_RT);
-            const float4 a1 = *reinterpret_cast<const float4*>(aT + k * MID_RT + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(hT + k * MID_RT);
-            const float4 h1 = *reinterpret_cast<const float4*>(hT + k * MID_RT + 4);
-            acc[0] = ffma2(ww2, make_float2(a0.x, a0.y), acc[0]); acc[1] = ffma2(ww2, make_float2(a0.z, a0.w), acc[1]);
-            acc[2] = ffma2(ww2, make_float2(a1.x, a1.y), acc[2]); acc[3] = ffma2(ww2, make_float2(a1.z, a1.w), acc[3]);
-            acc[0] = ffma2(ww3, make_float2(h0.x, h0.y), acc[0]); acc[1] = ffma2(ww3, make_float2(h0.z, h0.w), acc[1]);
-            acc[2] = ffma2(ww3, make_float2(h1.x, h1.y), acc[2]); acc[3] = ffma2(ww3, make_float2(h1.z, h1.w), acc[3]);
+    griddep_wait();
+    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
+        const int b = item / TILES;
+        const int r0 = (item % TILES) * MID_RT;
+        const int nr = min(MID_RT, NF - r0);
+        __syncthreads();
+        const int64_t row0 = (int64_t)b * NF + r0;
+        {
+            const int r = tid >> 5, k4 = tid & 31;
+            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Y + (row0 + r) * 128 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            A1[mid_aidx(M1_KS, k4 * 4 + 0, r)] = v.x; A1[mid_aidx(M1_KS, k4 * 4 + 1, r)] = v.y;
+            A1[mid_aidx(M1_KS, k4 * 4 + 2, r)] = v.z; A1[mid_aidx(M1_KS, k4 * 4 + 3, r)] = v.w;
         }
-#pragma unroll
-        for (int i = 0; i < MID_RT / 2; ++i) {
-            gt[(2 * i) * 256 + tid] = acc[i].x;
-            gt[(2 * i + 1) * 256 + tid] = acc[i].y;
+        mbar_wait(&wbar, 0);
+        __syncthreads();
+        {
+            const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
+            float v[MID_RT * M1_C];
+            mid_mm<M1_C, M1_KQ, M1_KS, M1_N>(W1, A1, tid >> 4, tid & 15, v);
+            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl1 + n1));
+            const float2 xo = (r1 < nr) ? *reinterpret_cast<const float2*>(X + (row0 + r1) * 64 + n1) : make_float2(0.f, 0.f);
+            const float2 x1v = make_float2(xo.x + v[0] + bias.x, xo.y + v[1] + bias.y);
+            *reinterpret_cast<float2*>(x1s + r1 * 64 + n1) = x1v;
+            if (r1 < nr) *reinterpret_cast<float2*>(X + (row0 + r1) * 64 + n1) = x1v;
         }
-    }
-    __syncthreads();
-    // ---- phase 4: LSTM cell; thread (hidden unit c, row pair) -------------------------------------
-    {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int r = rp * 2 + u;
-            const float4 g4 = *reinterpret_cast<const float4*>(gt + r * 256 + c * 4);      // i, f, g, o
-            const float gi = fast_sigmoid(g4.x), gf = fast_sigmoid(g4.y), gg = fast_tanh(g4.z), go = fast_sigmoid(g4.w);
-            const float cold = (r < nr) ? cst[(r0 + r) * 64 + c] : 0.f;
-            const float cn = gf * cold + gi * gg;
-            const float hn = go * fast_tanh(cn);
-            if (r < nr) { cst[(r0 + r) * 64 + c] = cn; hst[(r0 + r) * 64 + c] = hn; }
-            x2T[c * MID_RT + r] = hn;       // stage h' k-major (x2T is free until phase 5 writes it)
+        __syncthreads();
+        {
+            const int r = tid >> 5, lane = tid & 31;
+            const float v0 = x1s[r * 64 + lane], v1 = x1s[r * 64 + lane + 32];
+            const float mu = warp_sum(v0 + v1) * (1.f / 64.f);
+            const float d0 = v0 - mu, d1 = v1 - mu;
+            const float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+            A3[mid_aidx(M3_KS, lane, r)] = d0 * rs * __ldg(w.ln2_g + lane) + __ldg(w.ln2_b + lane);
+            A3[mid_aidx(M3_KS, lane + 32, r)] = d1 * rs * __ldg(w.ln2_g + lane + 32) + __ldg(w.ln2_b + lane + 32);
+        }
+        __syncthreads();
+        {
+            float v[MID_RT * M3_C];
+            const int jp = tid >> 3, r = tid & 7;
+            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(W3a, A3, jp, r, v);
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8 + 4));
+            if (r < nr) {
+                float4* gp = reinterpret_cast<float4*>(GI + (row0 + r) * 256 + jp * 8);
+                gp[0] = make_float4(v[0] + ba.x, v[1] + ba.y, v[2] + ba.z, v[3] + ba.w);
+                gp[1] = make_float4(v[4] + bb.x, v[5] + bb.y, v[6] + bb.z, v[7] + bb.w);
+            }
         }
     }
-    __syncthreads();
-    // ---- phase 5: X2 = X1 + h' W4 + b ----------------------------------------------------------------
-    float2 x2v;
-    {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) {
-            const float wv = W4[k * 64 + c];
-            const float2 hv = *reinterpret_cast<const float2*>(x2T + k * MID_RT + rp * 2);
-            acc = ffma2(make_float2(wv, wv), hv, acc);
-        }
-        const float bias = __ldg(w.bl2 + c);
-        x2v = make_float2(x1[(rp * 2) * 64 + c] + acc.x + bias, x1[(rp * 2 + 1) * 64 + c] + acc.y + bias);
-        if (rp * 2 < nr) X[(row0 + rp * 2) * 64 + c] = x2v.x;
-        if (rp * 2 + 1 < nr) X[(row0 + rp * 2 + 1) * 64 + c] = x2v.y;
+}
+
+__global__ void __launch_bounds__(256)
+mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, float* __restrict__ state, int64_t sstride, int blk,
+             BlockWeights w, int n_streams) {
+    extern __shared__ __align__(16) float sm[];
+    float* W3b = sm;                                  // W_hh, k-sliced
+    float* A3 = W3b + (MID_W5 - MID_W3B);             // h, k-sliced
+    __shared__ __align__(8) unsigned long long wbar;
+    griddep_launch();
+    const int tid = threadIdx.x;
+    constexpr int TILES = (NF + MID_RT - 1) / MID_RT;
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&wbar, (MID_W5 - MID_W3B) * 4);
+        tma_load_1d(W3b, w.mid_pack + MID_W3B, (MID_W5 - MID_W3B) * 4, &wbar);
     }
-    __syncthreads();                      // everyone has consumed h' from x2T
-    *reinterpret_cast<float2*>(x2T + c * MID_RT + rp * 2) = x2v;
     __syncthreads();
-    // ---- phase 6: P = PReLU(X2 W5 + b); item = (column n, row pair) ---------------------------------
-    for (int it = tid; it < NQKV * (MID_RT / 2); it += 256) {
-        const int n = it % NQKV, q = it / NQKV;
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) {
-            const float wv = W5[k * NQKV + n];
-            const float2 xv = *reinterpret_cast<const float2*>(x2T + k * MID_RT + q * 2);
-            acc = ffma2(make_float2(wv, wv), xv, acc);
+    griddep_wait();
+    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
+        const int b = item / TILES;
+        const int r0 = (item % TILES) * MID_RT;
+        const int nr = min(MID_RT, NF - r0);
+        __syncthreads();
+        float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+        float* hst = sb + BK_H;
+        float* cst = sb + BK_C;
+        const int64_t row0 = (int64_t)b * NF + r0;
+        if (tid < 128) {
+            const int r = tid >> 4, k4 = tid & 15;
+            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            A3[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; A3[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
+            A3[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; A3[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
         }
-        const float bias = __ldg(w.bqkv + n);
-        const float slope = __ldg(w.slopes + (n < 24 ? 0 : (n < 48 ? 1 : 2)));
-        if (q * 2 < nr) QKV[(row0 + q * 2) * NQKV + n] = prelu(acc.x + bias, slope);
-        if (q * 2 + 1 < nr) QKV[(row0 + q * 2 + 1) * NQKV + n] = prelu(acc.y + bias, slope);
+        const int jp = tid >> 3, r = tid & 7;
+        // this lane's input-side gate pre-activations and cell state: loaded now, used after the product
+        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+        float2 cold = make_float2(0.f, 0.f);
+        if (r < nr) {
+            const float4* gp = reinterpret_cast<const float4*>(GI + (row0 + r) * 256 + jp * 8);
+            ga = gp[0]; gb = gp[1];
+            cold = *reinterpret_cast<const float2*>(cst + (r0 + r) * 64 + jp * 2);
+        }
+        mbar_wait(&wbar, 0);
+        __syncthreads();
+        float v[MID_RT * M3_C];
+        mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(W3b, A3, jp, r, v);
+        const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
+        const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
+        const float c0 = gf0 * cold.x + gi0 * gg0, c1 = gf1 * cold.y + gi1 * gg1;
+        const float h0 = go0 * fast_tanh(c0), h1 = go1 * fast_tanh(c1);
+        if (r < nr) {
+            *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = make_float2(c0, c1);
+            *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(Hn + (row0 + r) * 64 + jp * 2) = make_float2(h0, h1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restrict__ QKV, BlockWeights w, int n_streams) {
+    extern __shared__ __align__(16) float sm[];
+    float* W5 = sm;                                   // inter linear | q|k|v projections, k-sliced
+    float* W6 = W5 + (MID_W6 - MID_W5);
+    float* A5 = W5 + (MID_PACK - MID_W5);
+    float* A6 = A5 + MID_A5;
+    __shared__ __align__(8) unsigned long long wbar;
+    griddep_launch();
+    const int tid = threadIdx.x;
+    constexpr int TILES = (NF + MID_RT - 1) / MID_RT;
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&wbar, (MID_PACK - MID_W5) * 4);
+        tma_load_1d(W5, w.mid_pack + MID_W5, (MID_PACK - MID_W5) * 4, &wbar);
+    }
+    __syncthreads();
+    griddep_wait();
+    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
+        const int b = item / TILES;
+        const int r0 = (item % TILES) * MID_RT;
+        const int nr = min(MID_RT, NF - r0);
+        __syncthreads();
+        const int64_t row0 = (int64_t)b * NF + r0;
+        if (tid < 128) {
+            const int r = tid >> 4, k4 = tid & 15;
+            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Hn + (row0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            A5[mid_aidx(M5_KS, k4 * 4 + 0, r)] = v.x; A5[mid_aidx(M5_KS, k4 * 4 + 1, r)] = v.y;
+            A5[mid_aidx(M5_KS, k4 * 4 + 2, r)] = v.z; A5[mid_aidx(M5_KS, k4 * 4 + 3, r)] = v.w;
+        }
+        const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
+        const float2 x1v = (r1 < nr) ? *reinterpret_cast<const float2*>(X + (row0 + r1) * 64 + n1) : make_float2(0.f, 0.f);
+        mbar_wait(&wbar, 0);
+        __syncthreads();
+        {
+            float v[MID_RT * M5_C];
+            mid_mm<M5_C, M5_KQ, M5_KS, M5_N>(W5, A5, tid >> 4, tid & 15, v);
+            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl2 + n1));
+            const float2 x2v = make_float2(x1v.x + v[0] + bias.x, x1v.y + v[1] + bias.y);
+            if (r1 < nr) *reinterpret_cast<float2*>(X + (row0 + r1) * 64 + n1) = x2v;
+            A6[mid_aidx(M6_KS, n1, r1)] = x2v.x;
+            A6[mid_aidx(M6_KS, n1 + 1, r1)] = x2v.y;
+        }
+        __syncthreads();
+        if (tid < (M6_N / M6_C) * M6_KQ) {
+            float v[MID_RT * M6_C];
+            const int cg = tid >> 3, r = tid & 7;
+            mid_mm<M6_C, M6_KQ, M6_KS, M6_N>(W6, A6, cg, r, v);
+            const float4 bias = __ldg(reinterpret_cast<const float4*>(w.bqkv + cg * 4));
+            const float slope = __ldg(w.slopes + (cg < 6 ? 0 : (cg < 12 ? 1 : 2)));
+            if (r < nr)
+                *reinterpret_cast<float4*>(QKV + (row0 + r) * NQKV + cg * 4) =
+                    make_float4(prelu(v[0] + bias.x, slope), prelu(v[1] + bias.y, slope), prelu(v[2] + bias.z, slope),
+                                prelu(v[3] + bias.w, slope));
+        }
     }
 }
 

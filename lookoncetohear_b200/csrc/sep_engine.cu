@@ -57,10 +57,20 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     cudaStream_t cap_stream = nullptr;
-    cudaStream_t pipe_streams[40] = {};
+    struct MidSrc { int64_t wl1, wih2, whh2t, wl2, wqkv, dst; };
+    std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
+    cudaStream_t pipe_streams[96] = {};
     std::vector<cudaEvent_t> pipe_events;
     int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
-    int pipe_alanes = 4;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
+    int pipe_alanes = 8;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
+    int pipe_skip = 0;            // DEBUG (timing experiments only): bit mask of pipeline stages NOT to launch
+    int pipe_pdl = 16;            // pipeline: stages launched with programmatic dependent launch (bit mask; 16 = mid_b)
+    bool pipe_split_mid = true;   // pipeline: mid section as mid_a | mid_b (serial) | mid_c
+    int pipe_qlanes = 3;     // qkv hops in flight per block (<= PIPE_QLANES)
+    int pipe_tlanes = 2;     // attention hops in flight per block (<= PIPE_TLANES)
+    int pipe_olanes = 4;     // attn_out hops in flight per block (<= PIPE_OLANES)
+    int pipe_flanes = 4;     // front_kernel hops in flight (<= PIPE_FLANES)
+    int pipe_blanes = 4;     // back_kernel hops in flight (<= PIPE_BLANES)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
@@ -144,7 +154,8 @@ static void build_layout(SepEngine* e) {
         bias(B + "intra_rnn.bias_ih_l0_reverse", b1 + 256, true);
         bias(B + "intra_rnn.bias_hh_l0_reverse", b1 + 256, true);
         bind(&W.wih1_t, wih1); bind(&W.b1, b1); bind(&W.whh1, whh1);
-        bind(&W.wl1_t, transposed(B + "intra_linear.weight", 64, 128, 64));
+        const int64_t wl1 = transposed(B + "intra_linear.weight", 64, 128, 64);
+        bind(&W.wl1_t, wl1);
         bind(&W.bl1, plain(B + "intra_linear.bias", 64));
         const int64_t wih2 = alloc(64 * 256), b2 = alloc(256), whh2 = alloc(256 * 64), whh2t = alloc(64 * 256);
         ih(B + "inter_rnn.weight_ih_l0", wih2, 256, 0);
@@ -159,7 +170,8 @@ static void build_layout(SepEngine* e) {
         bias(B + "inter_rnn.bias_ih_l0", b2, true);
         bias(B + "inter_rnn.bias_hh_l0", b2, true);
         bind(&W.wih2_t, wih2); bind(&W.b2, b2); bind(&W.whh2, whh2);
-        bind(&W.wl2_t, transposed(B + "inter_linear.weight", 64, 64, 64));
+        const int64_t wl2 = transposed(B + "inter_linear.weight", 64, 64, 64);
+        bind(&W.wl2_t, wl2);
         bind(&W.bl2, plain(B + "inter_linear.bias", 64));
         // Q | K | V projections -> one [64][112] k-major matrix
         const int64_t wqkv = alloc(64 * NQKV), bqkv = alloc(NQKV), slopes = alloc(4);
@@ -179,6 +191,9 @@ static void build_layout(SepEngine* e) {
         proj("attn_conv_K", NHEAD * QE, NHEAD * QE, 1);
         proj("attn_conv_V", NHEAD * VD, 2 * NHEAD * QE, 2);
         bind(&W.wqkv_t, wqkv); bind(&W.bqkv, bqkv); bind(&W.slopes, slopes);
+        const int64_t midp = alloc(MID_PACK);
+        bind(&W.mid_pack, midp);
+        e->mid_src.push_back({wl1, wih2, whh2t, wl2, wqkv, midp});
         bind(&W.lnq_g, plain(B + "attn_conv_Q.3.norm.weight", QK_DIM));
         bind(&W.lnq_b, plain(B + "attn_conv_Q.3.norm.bias", QK_DIM));
         bind(&W.lnk_g, plain(B + "attn_conv_K.3.norm.weight", QK_DIM));
@@ -204,7 +219,7 @@ static void resolve_pointers(SepEngine* e) {
     fixp(w.wd); fixp(w.bd);
     for (auto& W : e->bw) {
         fixp(W.ln1_g); fixp(W.ln1_b); fixp(W.wih1_t); fixp(W.b1); fixp(W.whh1); fixp(W.wl1_t); fixp(W.bl1);
-        fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.whh2_t); fixp(W.wl2_t); fixp(W.bl2);
+        fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.whh2_t); fixp(W.mid_pack); fixp(W.wl2_t); fixp(W.bl2);
         fixp(W.wqkv_t); fixp(W.bqkv); fixp(W.slopes); fixp(W.lnq_g); fixp(W.lnq_b); fixp(W.lnk_g);
         fixp(W.lnk_b); fixp(W.lnv_g); fixp(W.lnv_b); fixp(W.wp_t); fixp(W.bp); fixp(W.lnp_g); fixp(W.lnp_b);
     }
@@ -247,6 +262,9 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
+    CK(cudaFuncSetAttribute(mid_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_A_SMEM));
+    CK(cudaFuncSetAttribute(mid_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_B_SMEM));
+    CK(cudaFuncSetAttribute(mid_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_C_SMEM));
     CK(configure_rows_gemm());
     CK(configure_lstm());
     g_attr_done = true;
@@ -326,8 +344,8 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_intra");
         if (fused_mid) {
-            CK(launch_k(pdl, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW,
-                        state, ss, b, W));
+            CK(launch_k(pdl, mid_kernel, dim3(std::min(148, B * ((NF + MID_RT - 1) / MID_RT))), dim3(256), MID_SMEM, st,
+                        (const float*)Y, X, QKVRAW, state, ss, b, W, B));
             MARK("mid");
         } else {
         g = GemmArgs{};
@@ -384,7 +402,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
-    CK(launch_k(pdl, back_kernel, dim3(T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
+    CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL * T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
                 a.pos_rel, 0, 1, 0, (int64_t)0));
     MARK("back");
 #undef MARK
@@ -405,15 +423,17 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
 constexpr int PIPE_MAX_FRAMES = 250;
-constexpr int PIPE_LANES = 4;      // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
-constexpr int PIPE_FLANES = 2;     // front_kernel lanes (frames of a group do not depend on each other there)
-constexpr int PIPE_BLANES = 3;     // back_kernel lanes
+constexpr int PIPE_LANES = 12;     // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
+constexpr int PIPE_FLANES = 4;     // max front_kernel lanes (frames of a group do not depend on each other there)
+constexpr int PIPE_BLANES = 6;     // max back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
-constexpr int PIPE_OLANES = 2;     // attn_out lanes (no hop-to-hop dependency)
-constexpr int PIPE_PER_BLOCK = PIPE_LANES + 3 + PIPE_OLANES;     // A lanes, B1 (mid), Bq (qkv), Ba (attention), Bo lanes (attn_out)
+constexpr int PIPE_QLANES = 3;     // max qkv lanes (hops write different ring rows; RING - ATT = 2 may run ahead of the attention)
+constexpr int PIPE_TLANES = 4;     // max attention lanes (attention only reads the rings)
+constexpr int PIPE_OLANES = 4;     // max attn_out lanes (no hop-to-hop dependency)
+constexpr int PIPE_PER_BLOCK = PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + PIPE_OLANES;   // A lanes, B1 (mid), Bq lanes (qkv), Ba lanes (attention), Bo lanes (attn_out)
 constexpr int PIPE_STREAMS = PIPE_BASE + 3 * PIPE_PER_BLOCK;
 constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites a ring row hop t's attention still reads
-static_assert(PIPE_STREAMS <= 40, "pipe_streams[]");
+static_assert(PIPE_STREAMS <= 96, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
 
@@ -426,6 +446,12 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     const int64_t ss = stream_stride(e->n_blocks);
     const int rows = B * NF;
     const int nsplit = attn_splits(B, 1);
+    // programmatic dependent launch, per stage: the kernel's prologue (weight staging) overlaps its stream predecessor's
+    // tail; every kernel reaches griddepcontrol.wait before it touches activations or state.  Worth it only on the
+    // serial stage (mid_b -> mid_b of the next hop): everywhere, the parked dependents hold shared memory and CTA
+    // slots the running kernels need (measured 14.0 vs 9.4 us per hop, profiles/r01f_pipeline_sweeps.jsonl)
+    const int ppdl = e->pipe_pdl;         // stage bit mask (same bits as pipe_skip)
+    const bool split_mid = e->pipe_split_mid && B * ((NF + MID_RT - 1) / MID_RT) <= 148;   // many streams: throughput, not latency
     float* state = a.state;
     for (int i = 0; i < PIPE_STREAMS; ++i)
         if (!e->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&e->pipe_streams[i], cudaStreamNonBlocking));
@@ -449,15 +475,18 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     };
     // stream map: [0] capture origin (fork / join / header advance), front lanes, back lanes, then per block:
     // PIPE_LANES x A, B1, B2a, B2b
-    auto sFront = [&](int k) { return e->pipe_streams[1 + k % PIPE_FLANES]; };
-    auto sBackL = [&](int k) { return e->pipe_streams[1 + PIPE_FLANES + k % PIPE_BLANES]; };
+    auto sFront = [&](int k) { return e->pipe_streams[1 + k % e->pipe_flanes]; };
+    auto sBackL = [&](int k) { return e->pipe_streams[1 + PIPE_FLANES + k % e->pipe_blanes]; };
     auto sA = [&](int b, int lane) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + lane]; };
     auto sB1 = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES]; };
-    auto sBq = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1]; };
-    auto sBa = [&](int b) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 2]; };
-    auto sBo = [&](int b, int k) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 3 + k % PIPE_OLANES]; };
+    auto sBq = [&](int b, int k) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1 + k % e->pipe_qlanes]; };
+    auto sBa = [&](int b, int k) { return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1 + PIPE_QLANES + k % e->pipe_tlanes]; };
+    auto sBo = [&](int b, int k) {
+        return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + k % e->pipe_olanes];
+    };
     // attention-done events of the last PIPE_QKV_AHEAD+1 hops per block (ring write-after-read guard)
     std::vector<std::vector<cudaEvent_t>> att_done(3, std::vector<cudaEvent_t>(K, nullptr));
+    std::vector<std::vector<cudaEvent_t>> qkv_done(3, std::vector<cudaEvent_t>(K, nullptr));
     std::vector<cudaEvent_t> out_done(K, nullptr);      // last block's attn_out of hop k (back(k) also reads hops k-1..k-3)
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
@@ -469,7 +498,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         // the device derives from the state header)
         const int lane = k % e->pipe_alanes;
         cudaStream_t sF = sFront(k), sBack = sBackL(k);
-        CK(launch_k(false, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs, a.x_len, X, state, ss, e->w, 1,
+        if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs, a.x_len, X, state, ss, e->w, 1,
                     a.pos_rel, a.emb, PRE, k, K, k * HOP));
         if (int rc = edge(sF, sA(0, lane))) return rc;
         for (int b = 0; b < 3; ++b) {
@@ -478,32 +507,49 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
             GemmArgs g{};
             g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
             g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
-            CK(launch_rows_gemm(g, st_a, false));
+            if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0));
             LstmArgs l{};
             l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
             l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
-            CK(launch_lstm_rec(l, st_a, false));
-            if (int rc = edge(st_a, sB1(b))) return rc;
-            CK(launch_k(false, mid_kernel, dim3((NF + MID_RT - 1) / MID_RT, B), dim3(256), MID_SMEM, sB1(b), (const float*)Y, X,
-                        QKVRAW, state, ss, b, W));
-            if (int rc = edge(sB1(b), sBq(b))) return rc;
-            if (k >= PIPE_QKV_AHEAD + 1) {          // the row this hop's K/V overwrite: attention of hop k-3 must be done
-                CK(cudaStreamWaitEvent(sBq(b), att_done[b][k - PIPE_QKV_AHEAD - 1], 0));
+            if (!(e->pipe_skip & 4)) CK(launch_lstm_rec(l, st_a, (ppdl & 4) != 0));
+            const dim3 mid_grid(std::min(148, B * ((NF + MID_RT - 1) / MID_RT)));
+            cudaStream_t st_q = sBq(b, k);
+            if (split_mid) {
+                // only the W_hh product + cell (mid_b) is serial per block; the rest rides on the parallel lanes.
+                // GI / H' live in the hop's GX slot, which the BiLSTM has finished with.
+                float* GI = GX; float* HN = GX + (int64_t)rows * 256;
+                if (!(e->pipe_skip & 8)) CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid, dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GI, W, B));
+                if (int rc = edge(st_a, sB1(b))) return rc;
+                if (!(e->pipe_skip & 16)) CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid, dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, state, ss, b, W, B));
+                if (int rc = edge(sB1(b), st_q)) return rc;
+                if (!(e->pipe_skip & 32)) CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid, dim3(256), MID_C_SMEM, st_q, (const float*)HN, X, QKVRAW, W, B));
+            } else {
+                if (int rc = edge(st_a, sB1(b))) return rc;
+                if (!(e->pipe_skip & 16)) CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid, dim3(256), MID_SMEM, sB1(b), (const float*)Y, X, QKVRAW, state, ss, b, W, B));
+                if (int rc = edge(sB1(b), st_q)) return rc;
             }
-            CK(launch_k(false, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, sBq(b), (const float*)X, (const float*)QKVRAW,
+            // the ring row this hop's K/V overwrite was last read by the attention of hop k-3: it and every earlier
+            // attention (one per attention lane) must be done
+            for (int d = 0; d < e->pipe_tlanes && k - PIPE_QKV_AHEAD - 1 - d >= 0; ++d)
+                CK(cudaStreamWaitEvent(st_q, att_done[b][k - PIPE_QKV_AHEAD - 1 - d], 0));
+            if (!(e->pipe_skip & 64)) CK(launch_k((ppdl & 64) != 0, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, st_q, (const float*)X, (const float*)QKVRAW,
                         Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
-            if (int rc = edge(sBq(b), sBa(b))) return rc;
+            if (int rc = next_event(&qkv_done[b][k])) return rc;
+            CK(cudaEventRecord(qkv_done[b][k], st_q));
+            // the attention reads this hop's ring row and the 49 before it: the other qkv lanes' latest hops must be in
+            cudaStream_t st_t = sBa(b, k);
+            for (int d = 0; d < e->pipe_qlanes && d <= k; ++d) CK(cudaStreamWaitEvent(st_t, qkv_done[b][k - d], 0));
             if (nsplit > 1) {
-                CK(launch_cluster(false, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, sBa(b),
+                if (!(e->pipe_skip & 128)) CK(launch_cluster((ppdl & 128) != 0, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, st_t,
                                   (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
             } else {
-                CK(launch_k(false, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, sBa(b), (const float*)Q, (const float*)nullptr,
+                if (!(e->pipe_skip & 128)) CK(launch_k((ppdl & 128) != 0, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, st_t, (const float*)Q, (const float*)nullptr,
                             (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
             }
             if (int rc = next_event(&att_done[b][k])) return rc;
-            CK(cudaEventRecord(att_done[b][k], sBa(b)));
+            CK(cudaEventRecord(att_done[b][k], st_t));
             CK(cudaStreamWaitEvent(sBo(b, k), att_done[b][k], 0));
-            CK(launch_k(false, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X, (const float*)state, ss,
+            if (!(e->pipe_skip & 256)) CK(launch_k((ppdl & 256) != 0, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X, (const float*)state, ss,
                         W, b == 0 ? 1 : 0, 1));
             if (b < 2) {
                 if (int rc = edge(sBo(b, k), sA(b + 1, lane))) return rc;
@@ -511,11 +557,11 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 if (int rc = next_event(&out_done[k])) return rc;
                 CK(cudaEventRecord(out_done[k], sBo(b, k)));
                 CK(cudaStreamWaitEvent(sBack, out_done[k], 0));
-                // the previous hop's output sits on the other attn_out lane: wait for it too (k-2, k-3 follow in-lane)
-                if (k >= 1) CK(cudaStreamWaitEvent(sBack, out_done[k - 1], 0));
+                // the three previous hops' outputs (deconv / overlap-add context) sit on other attn_out lanes
+                for (int d = 1; d <= 3 && d <= k; ++d) CK(cudaStreamWaitEvent(sBack, out_done[k - d], 0));
             }
         }
-        CK(launch_k(false, back_kernel, dim3(1, B), dim3(256), BACK_SMEM, sBack, (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state,
+        if (!(e->pipe_skip & 512)) CK(launch_cluster((ppdl & 512) != 0, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL, B), dim3(256), BACK_SMEM, sBack, (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state,
                     ss, e->w, 1, a.pos_rel, k, K, k * HOP, slot));
     }
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // join
@@ -656,6 +702,21 @@ int l2h_sep_commit_weights(void* handle, void* stream) {
         if (kv.second.accumulate) std::fill(e->host.begin() + kv.second.off, e->host.begin() + kv.second.off + 256, 0.f);
     for (auto& kv : e->slots)
         if (kv.second.accumulate) kv.second.repack(kv.second.raw.data(), e->host.data());
+    for (const auto& m : e->mid_src) {      // k-sliced, bank-padded copies for mid_kernel (layout: mid_kernel.cuh)
+        float* h = e->host.data();
+        std::fill(h + m.dst, h + m.dst + MID_PACK, 0.f);
+        for (int k = 0; k < M1_K; ++k)
+            for (int n = 0; n < M1_N; ++n) h[m.dst + MID_W1 + mid_widx(M1_KS, M1_N, k, n)] = h[m.wl1 + (int64_t)k * 64 + n];
+        for (int k = 0; k < M3_K; ++k)
+            for (int n = 0; n < M3_N; ++n) {
+                h[m.dst + MID_W3A + mid_widx(M3_KS, M3_N, k, n)] = h[m.wih2 + (int64_t)k * 256 + n];
+                h[m.dst + MID_W3B + mid_widx(M3_KS, M3_N, k, n)] = h[m.whh2t + (int64_t)k * 256 + n];
+            }
+        for (int k = 0; k < M5_K; ++k)
+            for (int n = 0; n < M5_N; ++n) h[m.dst + MID_W5 + mid_widx(M5_KS, M5_N, k, n)] = h[m.wl2 + (int64_t)k * 64 + n];
+        for (int k = 0; k < M6_K; ++k)
+            for (int n = 0; n < M6_N; ++n) h[m.dst + MID_W6 + mid_widx(M6_KS, M6_N, k, n)] = h[m.wqkv + (int64_t)k * NQKV + n];
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool first = (e->dev == nullptr);
     if (first) CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
@@ -709,7 +770,10 @@ int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* off, 
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !n) return fail(1, "bad argument");
-    *n = 1 + e->n_blocks * (frames == 1 && e->use_mid ? 6 : 9 + (frames > 1 ? 1 : 0)) + 1;
+    // one-hop calls: 6 kernels per block fused (gemm, bilstm, mid, qkv, attn, attn_out); streams of one-hop calls run
+    // through the pipelined graph, where the mid section is three kernels (mid_a | mid_b | mid_c) -> 8 per block
+    const int one_hop = e->use_mid ? ((e->use_pipe && e->pipe_split_mid) ? 8 : 6) : 9;
+    *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
     return 0;
 }
 
@@ -806,9 +870,23 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !name) return fail(1, "bad argument");
     const std::string n(name);
-    if (n == "pipeline") e->use_pipe = value != 0;
+    if (n == "defaults") {                      // lane counts and mid split back to the built-in defaults
+        const SepEngine d{};
+        e->pipe_alanes = d.pipe_alanes; e->pipe_qlanes = d.pipe_qlanes; e->pipe_tlanes = d.pipe_tlanes;
+        e->pipe_olanes = d.pipe_olanes; e->pipe_flanes = d.pipe_flanes; e->pipe_blanes = d.pipe_blanes;
+        e->pipe_split_mid = d.pipe_split_mid; e->pipe_frames = d.pipe_frames; e->pipe_skip = 0; e->pipe_pdl = d.pipe_pdl;
+    }
+    else if (n == "pipeline") e->use_pipe = value != 0;
     else if (n == "pipeline_frames") e->pipe_frames = std::max(2, std::min(PIPE_MAX_FRAMES, (int)value));
     else if (n == "pipeline_lanes") e->pipe_alanes = std::max(1, std::min(PIPE_LANES, (int)value));
+    else if (n == "pipeline_debug_skip") e->pipe_skip = value;
+    else if (n == "pipeline_pdl") e->pipe_pdl = value;
+    else if (n == "pipeline_split_mid") e->pipe_split_mid = value != 0;
+    else if (n == "pipeline_qkv_lanes") e->pipe_qlanes = std::max(1, std::min(PIPE_QLANES, (int)value));
+    else if (n == "pipeline_attn_lanes") e->pipe_tlanes = std::max(1, std::min(PIPE_TLANES, (int)value));
+    else if (n == "pipeline_out_lanes") e->pipe_olanes = std::max(1, std::min(PIPE_OLANES, (int)value));
+    else if (n == "pipeline_front_lanes") e->pipe_flanes = std::max(1, std::min(PIPE_FLANES, (int)value));
+    else if (n == "pipeline_back_lanes") e->pipe_blanes = std::max(1, std::min(PIPE_BLANES, (int)value));
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
     else return fail(2, "unknown option: " + n);

@@ -33,7 +33,8 @@ struct BlockWeights {
     const float* wih2_t;              // [64][256]
     const float* b2;                  // [256]
     const float* whh2;                // [256][64]   (row = gate column j*4+q)
-    const float* whh2_t;              // [64][256]   the same matrix k-major (mid_kernel)
+    const float* whh2_t;              // [64][256]   the same matrix k-major (source of mid_pack)
+    const float* mid_pack;            // [MID_PACK]  k-sliced copies of wl1_t, [wih2_t ; whh2_t], wl2_t, wqkv_t (mid_kernel.cuh)
     const float* wl2_t;               // [64][64]
     const float* bl2;
     const float* wqkv_t;              // [64][112]   cols: Q(h*6+e) | K(h*6+e) | V(h*16+c)
@@ -820,35 +821,53 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
 // ------------------------------------------------------------------------------------------
 // K5 back: causal 3x3 transposed conv (64 -> 4) + Re/Im regroup + synthesis filterbank +
 // overlap-add   (tfgridnet_causal.py:256-273; net.py:61 drops the look-ahead tail).
-// grid (T, B), 256 threads.  y: [B][NSRC][y_len], frame t writes samples 128 t .. 128 t + 127.
-// The frames of X (4 x 24.8 KB, contiguous) arrive by TMA; the synthesis filterbank (149 KB) is then
-// streamed by TMA in two halves through the same shared-memory region once the deconv is done.
+// grid (BACK_CL * T, B) in clusters of BACK_CL CTAs, 256 threads.  y: [B][NSRC][y_len], frame t writes
+// samples 128 t .. 128 t + 127.  One frame is one cluster: CTA `part` owns a quarter of the frequency bins
+// -- it stages those rows (+ halo) of the four frames it needs by TMA, runs the deconv for them, and sums
+// the synthesis filterbank over ITS rows only (its 2 x ~24 filter rows, 37 KB, prefetched by TMA before the
+// dependency wait).  The four partial windows meet in CTA 0 through distributed shared memory, in a fixed
+// order, and CTA 0 does the overlap-add and the store.  (v1 ran the frame in one CTA: 28 us per hop, the
+// slowest stage of the one-hop pipeline once the mid section was split.)
 // The last CTA to finish advances the state header (pos += T, ncalls += 1).
-constexpr int BACK_WS_HALF = NROW / 2;      // 97 filter rows per half
-constexpr size_t BACK_SMEM = (size_t)(4 * 99 * 64 + 2 * NSRC * NROW + NSRC * NFFT) * sizeof(float);
-static_assert(BACK_WS_HALF * NFFT <= 4 * 99 * 64, "filter half must fit in the frame region");
+constexpr int BACK_CL = 4;
+constexpr int BACK_FMAX = (NF + BACK_CL - 1) / BACK_CL;       // 25 bins per CTA at most
+constexpr size_t BACK_SMEM = (size_t)(4 * (BACK_FMAX + 2) * 64 + 2 * BACK_FMAX * NFFT + 2 * NSRC * NROW + NSRC * NFFT) * sizeof(float);
+
+__device__ __forceinline__ int back_f0(int part) { return (part * NF) / BACK_CL; }
 
 __global__ void __launch_bounds__(256)
 back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride,
             int y_len, float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int frame_k,
             int frames_total, int sample_off, int64_t hist_stride) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;                       // [4 slots: frame t-3+i][99 = 1 + f + 1][64]; later: filter halves
-    float* R = Xs + 4 * 99 * 64;          // [2: frame t-1, t][2 ears][194]
-    float* wacc = R + 2 * NSRC * NROW;    // [2 ears][192] partial synthesis sums
-    __shared__ __align__(8) unsigned long long bars[3];
-    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    float* Xs = sm;                                    // [4 slots: frame t-3+i][nf + 2 rows: f0-1 .. f1][64]
+    float* Wf = Xs + 4 * (BACK_FMAX + 2) * 64;         // [2: re, im][nf][192] this CTA's synthesis filter rows
+    float* R = Wf + 2 * BACK_FMAX * NFFT;              // [2: frame t-1, t][2 ears][194]  (own bins only)
+    float* wacc = R + 2 * NSRC * NROW;                 // [2 ears][192] partial synthesis sums
+    __shared__ __align__(8) unsigned long long bars[2];
+    const int part = (int)cluster.block_rank();
+    const int t = blockIdx.x / BACK_CL, b = blockIdx.y, tid = threadIdx.x;
+    const int f0 = back_f0(part), f1 = back_f0(part + 1), nf = f1 - f0;
+    const int ld = nf + 2;                             // staged rows per frame slot: bins f0-1 .. f1
     griddep_launch();
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init();
+        // this CTA's filter rows: weights, so they can be on their way before the dependency wait
+        mbar_expect_tx(&bars[1], 2 * nf * NFFT * 4);
+        tma_load_1d(Wf, w.ws + (int64_t)f0 * NFFT, nf * NFFT * 4, &bars[1]);
+        tma_load_1d(Wf + nf * NFFT, w.ws + (int64_t)(NF + f0) * NFFT, nf * NFFT * 4, &bars[1]);
+    }
     // group bookkeeping as in front_kernel: gi = frame index in the group, frames before the group come
     // from the deconv tails the previous group left, frames inside it from X (T > 1) or from the
     // workspace slots of the previous one-frame calls of the pipelined graph (hist_stride apart)
     const int gi = frame_k + t, GN = (frames_total > 1) ? frames_total : T;
-    // zero the frequency padding rows (0 and 98) of every slot and whole slots that stay empty
-    for (int i = tid; i < 4 * 99 * 64; i += 256) {
-        const int slot = i / (99 * 64), r = (i / 64) % 99;
-        const int g = gi - 3 + slot;
-        if (r == 0 || r == 98 || g < -2) Xs[i] = 0.f;
+    // zero the halo rows that fall outside 0 .. 96 and whole slots that stay empty
+    for (int i = tid; i < 4 * ld * 64; i += 256) {
+        const int slot = i / (ld * 64), r = (i / 64) % ld;
+        const int g = gi - 3 + slot, f = f0 - 1 + r;
+        if (f < 0 || f >= NF || g < -2) Xs[i] = 0.f;
     }
     float wr[2][36];
     {
@@ -868,11 +887,12 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
     const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
     float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
-    {
+    const int lo = max(f0 - 1, 0), hi = min(f1 + 1, NF);          // staged bins that exist: [lo, hi)
+    if (tid == 0) {
         int nfr = 0;
         for (int slot = 0; slot < 4; ++slot) nfr += (gi - 3 + slot >= -2) ? 1 : 0;
-        if (tid == 0) { fence_proxy_async(); mbar_expect_tx(&bars[0], nfr * FC * 4); }
-        __syncthreads();
+        fence_proxy_async();
+        mbar_expect_tx(&bars[0], nfr * (hi - lo) * 64 * 4);
         for (int slot = 0; slot < 4; ++slot) {
             const int g = gi - 3 + slot;
             if (g < -2) continue;
@@ -880,22 +900,22 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
             if (g < 0) src = db + (2 + g) * FC;
             else if (frames_total > 1) src = X - (int64_t)(3 - slot) * hist_stride + (int64_t)b * FC;   // slot of one-frame call g
             else src = X + ((int64_t)b * T + (t - 3 + slot)) * FC;
-            tma_load_split(Xs + (slot * 99 + 1) * 64, src, FC * 4, &bars[0], tid, 256);
+            tma_load_1d(Xs + (slot * ld + (lo - (f0 - 1))) * 64, src + lo * 64, (hi - lo) * 64 * 4, &bars[0]);
         }
     }
     mbar_wait(&bars[0], 0);
-    // deconv for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
+    // deconv of the own bins for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
     {
         const int warp = tid >> 5, lane = tid & 31;
         for (int fi = (gi >= 1 ? 0 : 1); fi < 2; ++fi) {
-            for (int f = warp; f < NF; f += 8) {
+            for (int f = f0 + warp; f < f1; f += 8) {
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        // frame (t-1+fi) - i  -> slot (2 + fi - i) ; freq f+1-j -> padded row f+2-j
-                        const float* xp = Xs + ((2 + fi - i) * 99 + (f + 2 - j)) * 64;
+                        // frame (t-1+fi) - i  -> slot (2 + fi - i) ; bin f+1-j -> staged row (f+1-j) - (f0-1)
+                        const float* xp = Xs + ((2 + fi - i) * ld + (f + 2 - j - f0)) * 64;
                         const float x0 = xp[lane], x1 = xp[lane + 32];
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
@@ -911,57 +931,63 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
                 }
             }
         }
-        if (gi == 0)
-            for (int i = tid; i < NSRC * NROW; i += 256) R[i] = ib[i];
+        if (gi == 0)                                   // the previous group's last spectrum (own bins)
+            for (int i = tid; i < NSRC * 2 * nf; i += 256) {
+                const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
+                R[idx] = ib[idx];
+            }
     }
     // next deconv tails (frames GN-2, GN-1) come straight from the staged frames of the group's last frame
     if (gi == GN - 1) {
-        for (int i = tid; i < FC / 4; i += 256) {
-            reinterpret_cast<float4*>(db_next)[i] = reinterpret_cast<const float4*>(Xs + (2 * 99 + 1) * 64)[i];
-            reinterpret_cast<float4*>(db_next + FC)[i] = reinterpret_cast<const float4*>(Xs + (3 * 99 + 1) * 64)[i];
+        for (int i = tid; i < nf * 16; i += 256) {
+            const int r = i / 16, c4 = i % 16;
+            reinterpret_cast<float4*>(db_next + (f0 + r) * 64)[c4] = reinterpret_cast<const float4*>(Xs + (2 * ld + 1 + r) * 64)[c4];
+            reinterpret_cast<float4*>(db_next + FC + (f0 + r) * 64)[c4] = reinterpret_cast<const float4*>(Xs + (3 * ld + 1 + r) * 64)[c4];
         }
     }
-    __syncthreads();                        // R complete; nobody reads the frame region any more
-    // synthesis: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}; filters streamed in two halves
-    float part[2] = {0.f, 0.f};             // this thread's outputs: item = tid and tid + 256 of (ear, n)
-    for (int half = 0; half < 2; ++half) {
-        fence_proxy_async();                // the region was read through the generic proxy until now
-        if (tid == 0) mbar_expect_tx(&bars[1 + half], BACK_WS_HALF * NFFT * 4);
-        __syncthreads();
-        tma_load_split(Xs, w.ws + (int64_t)half * BACK_WS_HALF * NFFT, BACK_WS_HALF * NFFT * 4, &bars[1 + half], tid, 256);
-        mbar_wait(&bars[1 + half], 0);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int item = tid + 256 * u;
-            if (item < NSRC * NFFT) {
-                const int ear = item / NFFT, n = item % NFFT;
-                const float* rr = R + (((n < HOP) ? 1 : 0) * NSRC + ear) * NROW + half * BACK_WS_HALF;
-                float acc = part[u];
-#pragma unroll 8
-                for (int r = 0; r < BACK_WS_HALF; ++r) acc = fmaf(rr[r], Xs[r * NFFT + n], acc);
-                part[u] = acc;
-            }
-        }
-        __syncthreads();                    // everybody is done with this half before it is overwritten
-    }
+    __syncthreads();                        // R (own bins) complete
+    // synthesis over the own filter rows: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}
+    mbar_wait(&bars[1], 0);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int item = tid + 256 * u;
-        if (item < NSRC * NFFT) wacc[item] = part[u];
-    }
-    __syncthreads();
-    for (int i = tid; i < NSRC * HOP; i += 256) {
-        const int ear = i / HOP, n = i % HOP;
-        const int s = HOP * t + n + soff;
-        if (s < y_len) {
-            float v = wacc[ear * NFFT + n];
-            if (n < LOOKAHEAD) v += wacc[ear * NFFT + HOP + n];     // overlap-add of the previous frame's tail
-            y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
+        if (item < NSRC * NFFT) {
+            const int ear = item / NFFT, n = item % NFFT;
+            const float* rr = R + (((n < HOP) ? 1 : 0) * NSRC + ear) * NROW + f0;
+            float acc = 0.f;
+            for (int ri = 0; ri < 2; ++ri) {
+                const float* wf = Wf + ri * nf * NFFT + n;
+                const float* rv = rr + ri * NF;
+#pragma unroll 5
+                for (int r = 0; r < nf; ++r) acc = fmaf(rv[r], wf[r * NFFT], acc);
+            }
+            wacc[item] = acc;
         }
     }
     if (gi == GN - 1)
-        for (int i = tid; i < NSRC * NROW; i += 256) ib_next[i] = R[NSRC * NROW + i];
-    __syncthreads();
+        for (int i = tid; i < NSRC * 2 * nf; i += 256) {
+            const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
+            ib_next[idx] = R[NSRC * NROW + idx];
+        }
+    cluster.sync();                         // all four partial windows are complete and visible cluster-wide
+    if (part == 0) {
+        for (int i = tid; i < NSRC * HOP; i += 256) {
+            const int ear = i / HOP, n = i % HOP;
+            const int s = HOP * t + n + soff;
+            if (s < y_len) {
+                float v = 0.f, tail = 0.f;
+#pragma unroll
+                for (int p = 0; p < BACK_CL; ++p) {
+                    const float* pw = cluster.map_shared_rank(wacc, p);
+                    v += pw[ear * NFFT + n];
+                    if (n < LOOKAHEAD) tail += pw[ear * NFFT + HOP + n];
+                }
+                if (n < LOOKAHEAD) v += tail;               // overlap-add of the previous frame's tail
+                y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
+            }
+        }
+    }
+    cluster.sync();                         // nobody leaves while CTA 0 may still read its shared memory
     // ordinary call: the last CTA to finish advances the header (a pipelined graph runs several back_kernels
     // at once and advances it with advance_header_kernel after all of its frames instead)
     if (frames_total == 1 && tid == 0) {

@@ -225,16 +225,26 @@ def test_device_streaming_entry_point(model, dev, cpc):
     _check(y2, y2_ref)
 
 
-def test_wavefront_pipeline_equals_sequential(model, dev):
+PIPE_OPTIONS = ("pipeline_lanes", "pipeline_qkv_lanes", "pipeline_attn_lanes", "pipeline_out_lanes", "pipeline_front_lanes",
+                "pipeline_back_lanes", "pipeline_split_mid", "pipeline_pdl")
+
+
+@pytest.mark.parametrize("lanes", [None, (8, 3, 4, 4, 4, 6, 1, 1023), (3, 1, 1, 1, 1, 2, 0, 16), (5, 2, 2, 3, 3, 3, 1, 0)],
+                         ids=["default", "max-lanes-pdl-everywhere", "few-lanes-fused-mid", "odd-lanes-no-pdl"])
+def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
     """One-hop calls captured as a (block, hop) wavefront graph must reproduce the strictly sequential
-    hop-by-hop run bit for bit (same kernels, same arithmetic, only the schedule differs), across a
-    group boundary (230 hops = 100 + 100 + 30) and for several streams; both match the oracle."""
+    hop-by-hop run bit for bit (same arithmetic, only the schedule and the kernel boundaries of the mid
+    section differ), across a group boundary (230 hops = 100 + 100 + 30), for several streams and for
+    several lane counts per stage (every lane count exercises other event edges); both match the oracle."""
     net, sd = model
     T, B = 230, 3
     x, _ = synth.mixture(B, 128 * T, seed0=91)
     e = synth.embedding(B, seed0=92)
     xd, ed = x.to(dev), e[:, 0].to(dev)
     try:
+        if lanes is not None:
+            for n, v in zip(PIPE_OPTIONS, lanes):
+                net.set_option(n, v)
         net.set_option("pipeline", 1)
         y_pipe = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
         st_pipe = net._last_stream_state.to_reference()
@@ -243,6 +253,7 @@ def test_wavefront_pipeline_equals_sequential(model, dev):
         st_seq = net._last_stream_state.to_reference()
     finally:
         net.set_option("pipeline", 1)
+        net.reset_options()
     assert torch.equal(y_pipe, y_seq)
     assert torch.equal(st_pipe["gridnet_bufs"]["buf2"]["K_buf"], st_seq["gridnet_bufs"]["buf2"]["K_buf"])
     assert torch.equal(st_pipe["deconv_buf"], st_seq["deconv_buf"])

@@ -1,5 +1,6 @@
-"""Pipeline sweep: hops per graph x BiLSTM lanes -> frames/s (device-resident clip, B=1), plus the CPU time
-the host spends inside l2h_sep_stream_dev (graph launches) per 500-hop clip."""
+"""Pipeline sweep: lane counts per stage -> frames/s (device-resident clip, B=1), plus the CPU time the host
+spends inside l2h_sep_stream_dev (graph launches) per 500-hop clip.
+    python tools/pipe_experiment.py [A:Q:T:O:F:B[:split_mid[:pdl]] ...]      lanes of BiLSTM : qkv : attention : attn_out : front : back"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,23 +14,28 @@ x, _ = synth.mixture(1, 64000)
 x = x.to(dev)
 emb = synth.embedding(1)[:, 0].to(dev)
 y = torch.empty(1, 2, 64000, device=dev)
-for frames in (100, 250):
-    for lanes in (3, 4):
-        net.set_option("pipeline_frames", frames)
-        net.set_option("pipeline_lanes", lanes)
-        best, cpu = None, None
-        for it in range(4):
-            st = net.init_buffers(1, dev)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            a.record()
-            net.stream_dev(x, emb, chunks_per_call=1, state=st, n_calls=500, out=y)
-            b.record()
-            t1 = time.perf_counter()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
-            if it > 0 and (best is None or ms < best):
-                best, cpu = ms, 1e3 * (t1 - t0)
-        print(json.dumps({"hops_per_graph": frames, "lstm_lanes": lanes, "frames_per_s": round(500 / (best * 1e-3)),
-                          "us_per_hop": round(1e3 * best / 500, 2), "host_ms_in_call": round(cpu, 2), "gpu_ms": round(best, 2)}))
+combos = sys.argv[1:] or ["8:3:2:4:4:4:1:0", "8:3:2:4:4:4:1:16", "8:3:3:4:4:4:1:16", "8:3:2:4:4:4:1:144", "8:3:2:4:4:4:1:20", "8:3:2:4:4:4:1:80", "8:3:4:4:4:6:1:16", "6:2:2:3:3:3:1:16", "8:3:2:4:4:4:1:528"]
+names = ("pipeline_lanes", "pipeline_qkv_lanes", "pipeline_attn_lanes", "pipeline_out_lanes", "pipeline_front_lanes",
+         "pipeline_back_lanes", "pipeline_split_mid", "pipeline_pdl")
+for combo in combos:
+    vals = [int(v) for v in combo.split(":")]
+    while len(vals) < 8:
+        vals.append(1)
+    for n, v in zip(names, vals):
+        net.set_option(n, v)
+    best, cpu = None, None
+    for it in range(4):
+        st = net.init_buffers(1, dev)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        net.stream_dev(x, emb, chunks_per_call=1, state=st, n_calls=500, out=y)
+        b.record()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if it > 0 and (best is None or ms < best):
+            best, cpu = ms, 1e3 * (t1 - t0)
+    print(json.dumps({"lanes_A:Q:T:O:F:B": combo, "frames_per_s": round(500 / (best * 1e-3)),
+                      "us_per_hop": round(1e3 * best / 500, 2), "host_ms_in_call": round(cpu, 2), "gpu_ms": round(best, 2)}), flush=True)
