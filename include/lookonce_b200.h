@@ -144,6 +144,10 @@ int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float
 /* number of kernels one l2h_sep_forward launches (for bench.py's gpu_launches) */
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);
 
+/* kernels this handle has launched so far (a CUDA-graph replay counts its kernel nodes); reset != 0 zeroes the
+   counter after reading.  bench.py's gpu_launches is read from here around the timed region. */
+int l2h_sep_launch_count(void* handle, int64_t* kernels, int32_t reset);
+
 /* ---- enrollment network (EmbedTFGridNet, configs/embed.json:5-10) ---------------------------- */
 typedef struct l2h_embed_config {
     int32_t embed_dim;  /* 256 */

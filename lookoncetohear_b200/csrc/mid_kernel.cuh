@@ -310,9 +310,11 @@ mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restri
     }
 }
 
+// n_hops consecutive hops per launch (GI / Hn of hop j at + j * hop_stride floats): h stays in shared memory and c in
+// registers between them, the state is read before the first and written after the last.
 __global__ void __launch_bounds__(256)
-mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, float* __restrict__ state, int64_t sstride, int blk,
-             BlockWeights w, int n_streams) {
+mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, int64_t hop_stride, int n_hops, float* __restrict__ state,
+             int64_t sstride, int blk, BlockWeights w, int n_streams) {
     extern __shared__ __align__(16) float sm[];
     float* W3b = sm;                                  // W_hh, k-sliced
     float* A3 = W3b + (MID_W5 - MID_W3B);             // h, k-sliced
@@ -344,26 +346,38 @@ mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, float* __rest
             A3[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; A3[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
         }
         const int jp = tid >> 3, r = tid & 7;
-        // this lane's input-side gate pre-activations and cell state: loaded now, used after the product
+        const bool live = r < nr;
+        // this lane's cell state and input-side gate pre-activations: loaded now, used after the product
+        float2 cc = live ? *reinterpret_cast<const float2*>(cst + (r0 + r) * 64 + jp * 2) : make_float2(0.f, 0.f);
+        float2 hh = make_float2(0.f, 0.f);
+        const float4* gp = reinterpret_cast<const float4*>(GI + (row0 + r) * 256 + jp * 8);
         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-        float2 cold = make_float2(0.f, 0.f);
-        if (r < nr) {
-            const float4* gp = reinterpret_cast<const float4*>(GI + (row0 + r) * 256 + jp * 8);
-            ga = gp[0]; gb = gp[1];
-            cold = *reinterpret_cast<const float2*>(cst + (r0 + r) * 64 + jp * 2);
-        }
+        if (live) { ga = gp[0]; gb = gp[1]; }
         mbar_wait(&wbar, 0);
-        __syncthreads();
-        float v[MID_RT * M3_C];
-        mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(W3b, A3, jp, r, v);
-        const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
-        const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
-        const float c0 = gf0 * cold.x + gi0 * gg0, c1 = gf1 * cold.y + gi1 * gg1;
-        const float h0 = go0 * fast_tanh(c0), h1 = go1 * fast_tanh(c1);
-        if (r < nr) {
-            *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = make_float2(c0, c1);
-            *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = make_float2(h0, h1);
-            *reinterpret_cast<float2*>(Hn + (row0 + r) * 64 + jp * 2) = make_float2(h0, h1);
+        for (int j = 0; j < n_hops; ++j) {
+            __syncthreads();                          // h of this hop is in A3
+            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;      // the next hop's input-side gates, in flight during the product
+            if (live && j + 1 < n_hops) {
+                const float4* np = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gp) + (int64_t)(j + 1) * hop_stride);
+                na = np[0]; nb = np[1];
+            }
+            float v[MID_RT * M3_C];
+            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(W3b, A3, jp, r, v);
+            const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
+            const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
+            cc = make_float2(gf0 * cc.x + gi0 * gg0, gf1 * cc.y + gi1 * gg1);
+            hh = make_float2(go0 * fast_tanh(cc.x), go1 * fast_tanh(cc.y));
+            if (live) *reinterpret_cast<float2*>(Hn + (int64_t)j * hop_stride + (row0 + r) * 64 + jp * 2) = hh;
+            ga = na; gb = nb;
+            if (j + 1 < n_hops) {
+                __syncthreads();                      // every lane has read the old h
+                A3[mid_aidx(M3_KS, jp * 2, r)] = hh.x;
+                A3[mid_aidx(M3_KS, jp * 2 + 1, r)] = hh.y;
+            }
+        }
+        if (live) {
+            *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = cc;
+            *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = hh;
         }
     }
 }

@@ -56,18 +56,22 @@ struct SepEngine {
     // CUDA-graph cache of whole kernel chains (the T=1 streaming chain is ~30 tiny kernels:
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
+    std::map<cudaGraphExec_t, int> graph_kernels;   // kernel nodes per cached graph
+    int64_t launch_count = 0;                       // kernels launched so far (graph replays counted by their kernel nodes)
     cudaStream_t cap_stream = nullptr;
     struct MidSrc { int64_t wl1, wih2, whh2t, wl2, wqkv, dst; };
     std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
     cudaStream_t pipe_streams[96] = {};
     std::vector<cudaEvent_t> pipe_events;
     int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
-    int pipe_alanes = 8;     // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
+    int pipe_alanes = 12;    // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
+    int pipe_midb_hops = 4;       // pipeline: consecutive hops one mid_b launch takes (<= PIPE_MIDB_MAX)
     int pipe_skip = 0;            // DEBUG (timing experiments only): bit mask of pipeline stages NOT to launch
     int pipe_pdl = 16;            // pipeline: stages launched with programmatic dependent launch (bit mask; 16 = mid_b)
     bool pipe_split_mid = true;   // pipeline: mid section as mid_a | mid_b (serial) | mid_c
     int pipe_qlanes = 3;     // qkv hops in flight per block (<= PIPE_QLANES)
-    int pipe_tlanes = 2;     // attention hops in flight per block (<= PIPE_TLANES)
+    int pipe_clanes = 2;     // mid_c hops in flight per block (<= PIPE_CLANES)
+    int pipe_tlanes = 3;     // attention hops in flight per block (<= PIPE_TLANES)
     int pipe_olanes = 4;     // attn_out hops in flight per block (<= PIPE_OLANES)
     int pipe_flanes = 4;     // front_kernel hops in flight (<= PIPE_FLANES)
     int pipe_blanes = 4;     // back_kernel hops in flight (<= PIPE_BLANES)
@@ -428,10 +432,12 @@ constexpr int PIPE_FLANES = 4;     // max front_kernel lanes (frames of a group 
 constexpr int PIPE_BLANES = 6;     // max back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
 constexpr int PIPE_QLANES = 3;     // max qkv lanes (hops write different ring rows; RING - ATT = 2 may run ahead of the attention)
+constexpr int PIPE_CLANES = 3;     // max mid_c lanes (no hop-to-hop dependency, not bound by the ring guard)
 constexpr int PIPE_TLANES = 4;     // max attention lanes (attention only reads the rings)
 constexpr int PIPE_OLANES = 4;     // max attn_out lanes (no hop-to-hop dependency)
-constexpr int PIPE_PER_BLOCK = PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + PIPE_OLANES;   // A lanes, B1 (mid), Bq lanes (qkv), Ba lanes (attention), Bo lanes (attn_out)
+constexpr int PIPE_PER_BLOCK = PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + PIPE_OLANES + PIPE_CLANES;   // A lanes, B1 (mid), Bq lanes (qkv), Ba lanes (attention), Bo lanes (attn_out)
 constexpr int PIPE_STREAMS = PIPE_BASE + 3 * PIPE_PER_BLOCK;
+constexpr int PIPE_MIDB_MAX = 8;   // max hops per mid_b launch
 constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites a ring row hop t's attention still reads
 static_assert(PIPE_STREAMS <= 96, "pipe_streams[]");
 
@@ -484,91 +490,144 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     auto sBo = [&](int b, int k) {
         return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + k % e->pipe_olanes];
     };
-    // attention-done events of the last PIPE_QKV_AHEAD+1 hops per block (ring write-after-read guard)
-    std::vector<std::vector<cudaEvent_t>> att_done(3, std::vector<cudaEvent_t>(K, nullptr));
+    auto sBc = [&](int b, int k) {
+        return e->pipe_streams[PIPE_BASE + b * PIPE_PER_BLOCK + PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + PIPE_OLANES + k % e->pipe_clanes];
+    };
+    // events: stage A (BiLSTM [+ mid_a]) done, qkv done, attention done, attn_out done -- per block and hop
+    std::vector<std::vector<cudaEvent_t>> a_done(3, std::vector<cudaEvent_t>(K, nullptr));
     std::vector<std::vector<cudaEvent_t>> qkv_done(3, std::vector<cudaEvent_t>(K, nullptr));
-    std::vector<cudaEvent_t> out_done(K, nullptr);      // last block's attn_out of hop k (back(k) also reads hops k-1..k-3)
+    std::vector<std::vector<cudaEvent_t>> att_done(3, std::vector<cudaEvent_t>(K, nullptr));
+    std::vector<std::vector<cudaEvent_t>> out_done(3, std::vector<cudaEvent_t>(K, nullptr));
+    auto record = [&](cudaEvent_t* ev, cudaStream_t s) -> int {
+        if (int rc = next_event(ev)) return rc;
+        CK(cudaEventRecord(*ev, s));
+        return 0;
+    };
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // fork: bring the worker streams into the capture
         if (int rc = edge(origin, e->pipe_streams[i])) return rc;
-    for (int k = 0; k < K; ++k) {
-        float* wsp = a.wsp + (int64_t)k * slot;
-        float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y; float* Z = wsp + ws.Z;
-        float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW; float* PRE = a.wsp + ws.PRE;   // PRE: front stream only
-        // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip position
-        // the device derives from the state header)
-        const int lane = k % e->pipe_alanes;
-        cudaStream_t sF = sFront(k), sBack = sBackL(k);
-        if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs, a.x_len, X, state, ss, e->w, 1,
-                    a.pos_rel, a.emb, PRE, k, K, k * HOP));
-        if (int rc = edge(sF, sA(0, lane))) return rc;
+    // The serial stage (mid_b) takes `mb` consecutive hops per launch: its ~3 us of launch overhead and its 64 KB of
+    // weights are paid once per batch, h stays in shared memory and c in registers from hop to hop.  A batch waits
+    // for stage A of all its hops; the upstream block is that far ahead anyway once the pipeline is full.
+    const int mb = split_mid ? std::max(1, std::min(e->pipe_midb_hops, PIPE_MIDB_MAX)) : 1;
+    const dim3 mid_grid(std::min(148, B * ((NF + MID_RT - 1) / MID_RT)));
+    float* PRE = a.wsp + ws.PRE;                                       // speaker-gate scratch: front stream only
+    for (int k0 = 0; k0 < K; k0 += mb) {
+        const int k1 = std::min(K, k0 + mb);                           // this batch: hops [k0, k1)
         for (int b = 0; b < 3; ++b) {
             const BlockWeights& W = e->bw[b];
-            cudaStream_t st_a = sA(b, lane);
-            GemmArgs g{};
-            g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
-            g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
-            if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0));
-            LstmArgs l{};
-            l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
-            l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
-            if (!(e->pipe_skip & 4)) CK(launch_lstm_rec(l, st_a, (ppdl & 4) != 0));
-            const dim3 mid_grid(std::min(148, B * ((NF + MID_RT - 1) / MID_RT)));
-            cudaStream_t st_q = sBq(b, k);
-            if (split_mid) {
+            // ---- stage A of every hop of the batch (parallel lanes) --------------------------------------
+            for (int k = k0; k < k1; ++k) {
+                float* wsp = a.wsp + (int64_t)k * slot;
+                float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y;
+                cudaStream_t st_a = sA(b, k % e->pipe_alanes);
+                if (b == 0) {
+                    // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip
+                    // position the device derives from the state header)
+                    cudaStream_t sF = sFront(k);
+                    if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs,
+                                                         a.x_len, X, state, ss, e->w, 1, a.pos_rel, a.emb, PRE, k, K, k * HOP));
+                    if (int rc = edge(sF, st_a)) return rc;
+                } else {
+                    CK(cudaStreamWaitEvent(st_a, out_done[b - 1][k], 0));
+                }
+                GemmArgs g{};
+                g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
+                g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
+                if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0));
+                LstmArgs l{};
+                l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
+                l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
+                if (!(e->pipe_skip & 4)) CK(launch_lstm_rec(l, st_a, (ppdl & 4) != 0));
                 // only the W_hh product + cell (mid_b) is serial per block; the rest rides on the parallel lanes.
                 // GI / H' live in the hop's GX slot, which the BiLSTM has finished with.
-                float* GI = GX; float* HN = GX + (int64_t)rows * 256;
-                if (!(e->pipe_skip & 8)) CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid, dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GI, W, B));
-                if (int rc = edge(st_a, sB1(b))) return rc;
-                if (!(e->pipe_skip & 16)) CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid, dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, state, ss, b, W, B));
-                if (int rc = edge(sB1(b), st_q)) return rc;
-                if (!(e->pipe_skip & 32)) CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid, dim3(256), MID_C_SMEM, st_q, (const float*)HN, X, QKVRAW, W, B));
-            } else {
-                if (int rc = edge(st_a, sB1(b))) return rc;
-                if (!(e->pipe_skip & 16)) CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid, dim3(256), MID_SMEM, sB1(b), (const float*)Y, X, QKVRAW, state, ss, b, W, B));
-                if (int rc = edge(sB1(b), st_q)) return rc;
+                if (split_mid && !(e->pipe_skip & 8))
+                    CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid, dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GX, W, B));
+                if (int rc = record(&a_done[b][k], st_a)) return rc;
             }
-            // the ring row this hop's K/V overwrite was last read by the attention of hop k-3: it and every earlier
-            // attention (one per attention lane) must be done
-            for (int d = 0; d < e->pipe_tlanes && k - PIPE_QKV_AHEAD - 1 - d >= 0; ++d)
-                CK(cudaStreamWaitEvent(st_q, att_done[b][k - PIPE_QKV_AHEAD - 1 - d], 0));
-            if (!(e->pipe_skip & 64)) CK(launch_k((ppdl & 64) != 0, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, st_q, (const float*)X, (const float*)QKVRAW,
-                        Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
-            if (int rc = next_event(&qkv_done[b][k])) return rc;
-            CK(cudaEventRecord(qkv_done[b][k], st_q));
-            // the attention reads this hop's ring row and the 49 before it: the other qkv lanes' latest hops must be in
-            cudaStream_t st_t = sBa(b, k);
-            for (int d = 0; d < e->pipe_qlanes && d <= k; ++d) CK(cudaStreamWaitEvent(st_t, qkv_done[b][k - d], 0));
-            if (nsplit > 1) {
-                if (!(e->pipe_skip & 128)) CK(launch_cluster((ppdl & 128) != 0, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B), dim3(256), 0, st_t,
-                                  (const float*)Q, (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
-            } else {
-                if (!(e->pipe_skip & 128)) CK(launch_k((ppdl & 128) != 0, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, st_t, (const float*)Q, (const float*)nullptr,
-                            (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
+            // ---- the serial stage: one launch for the batch ----------------------------------------------------
+            for (int k = k0; k < k1; ++k) CK(cudaStreamWaitEvent(sB1(b), a_done[b][k], 0));
+            {
+                float* wsp = a.wsp + (int64_t)k0 * slot;
+                float* GI = wsp + ws.GX; float* HN = GI + (int64_t)rows * 256;
+                if (split_mid) {
+                    if (!(e->pipe_skip & 16))
+                        CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid, dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, slot,
+                                    k1 - k0, state, ss, b, W, B));
+                } else if (!(e->pipe_skip & 16)) {
+                    CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid, dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y), wsp + ws.X,
+                                wsp + ws.QKVRAW, state, ss, b, W, B));
+                }
             }
-            if (int rc = next_event(&att_done[b][k])) return rc;
-            CK(cudaEventRecord(att_done[b][k], st_t));
-            CK(cudaStreamWaitEvent(sBo(b, k), att_done[b][k], 0));
-            if (!(e->pipe_skip & 256)) CK(launch_k((ppdl & 256) != 0, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X, (const float*)state, ss,
-                        W, b == 0 ? 1 : 0, 1));
-            if (b < 2) {
-                if (int rc = edge(sBo(b, k), sA(b + 1, lane))) return rc;
-            } else {
-                if (int rc = next_event(&out_done[k])) return rc;
-                CK(cudaEventRecord(out_done[k], sBo(b, k)));
-                CK(cudaStreamWaitEvent(sBack, out_done[k], 0));
-                // the three previous hops' outputs (deconv / overlap-add context) sit on other attn_out lanes
-                for (int d = 1; d <= 3 && d <= k; ++d) CK(cudaStreamWaitEvent(sBack, out_done[k - d], 0));
+            cudaEvent_t midb_done;
+            if (int rc = record(&midb_done, sB1(b))) return rc;
+            // ---- per hop: mid_c | qkv -> attention -> attn_out (parallel lanes with ring guards) -----------------
+            for (int k = k0; k < k1; ++k) {
+                float* wsp = a.wsp + (int64_t)k * slot;
+                float* X = wsp + ws.X; float* Z = wsp + ws.Z; float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW;
+                float* HN = wsp + ws.GX + (int64_t)rows * 256;
+                cudaStream_t st_q = sBq(b, k);
+                if (split_mid) {            // mid_c on its own lanes: the qkv lanes are held back by the ring guard
+                    cudaStream_t st_c = sBc(b, k);
+                    CK(cudaStreamWaitEvent(st_c, midb_done, 0));
+                    if (!(e->pipe_skip & 32))
+                        CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid, dim3(256), MID_C_SMEM, st_c, (const float*)HN, X, QKVRAW, W, B));
+                    if (int rc = edge(st_c, st_q)) return rc;
+                } else {
+                    CK(cudaStreamWaitEvent(st_q, midb_done, 0));
+                }
+                // the ring row this hop's K/V overwrite was last read by the attention of hop k-3: it and every earlier
+                // attention (one per attention lane) must be done
+                for (int d = 0; d < e->pipe_tlanes && k - PIPE_QKV_AHEAD - 1 - d >= 0; ++d)
+                    CK(cudaStreamWaitEvent(st_q, att_done[b][k - PIPE_QKV_AHEAD - 1 - d], 0));
+                if (!(e->pipe_skip & 64)) CK(launch_k((ppdl & 64) != 0, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, st_q, (const float*)X,
+                                                      (const float*)QKVRAW, Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
+                if (int rc = record(&qkv_done[b][k], st_q)) return rc;
+                // the attention reads this hop's ring row and the 49 before it: the other qkv lanes' latest hops must be in
+                cudaStream_t st_t = sBa(b, k);
+                for (int d = 0; d < e->pipe_qlanes && d <= k; ++d) CK(cudaStreamWaitEvent(st_t, qkv_done[b][k - d], 0));
+                if (nsplit > 1) {
+                    if (!(e->pipe_skip & 128)) CK(launch_cluster((ppdl & 128) != 0, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(1, NHEAD * ATT_CL, B),
+                                                                 dim3(256), 0, st_t, (const float*)Q, (const float*)nullptr, (const float*)nullptr,
+                                                                 (const float*)state, ss, b, Z, 1, k));
+                } else {
+                    if (!(e->pipe_skip & 128)) CK(launch_k((ppdl & 128) != 0, attn_kernel, dim3(1, NHEAD, B), dim3(256), 0, st_t, (const float*)Q,
+                                                           (const float*)nullptr, (const float*)nullptr, (const float*)state, ss, b, Z, 1, k));
+                }
+                if (int rc = record(&att_done[b][k], st_t)) return rc;
+                CK(cudaStreamWaitEvent(sBo(b, k), att_done[b][k], 0));
+                if (!(e->pipe_skip & 256)) CK(launch_k((ppdl & 256) != 0, attn_out_kernel, dim3(1, B), dim3(256), AOUT_SMEM, sBo(b, k), (const float*)Z, X,
+                                                       (const float*)state, ss, W, b == 0 ? 1 : 0, 1));
+                if (int rc = record(&out_done[b][k], sBo(b, k))) return rc;
             }
         }
-        if (!(e->pipe_skip & 512)) CK(launch_cluster((ppdl & 512) != 0, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL, B), dim3(256), BACK_SMEM, sBack, (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state,
-                    ss, e->w, 1, a.pos_rel, k, K, k * HOP, slot));
+        for (int k = k0; k < k1; ++k) {
+            float* X = a.wsp + (int64_t)k * slot + ws.X;
+            cudaStream_t sBack = sBackL(k);
+            // this hop's output and the three before it (deconv / overlap-add context) sit on different attn_out lanes
+            for (int d = 0; d <= 3 && d <= k; ++d) CK(cudaStreamWaitEvent(sBack, out_done[2][k - d], 0));
+            if (!(e->pipe_skip & 512)) CK(launch_cluster((ppdl & 512) != 0, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL, B), dim3(256), BACK_SMEM, sBack,
+                                                         (const float*)X, a.y, a.ybs, a.ycs, a.y_len, state, ss, e->w, 1, a.pos_rel, k, K, k * HOP, slot));
+        }
     }
     for (int i = 1; i < PIPE_STREAMS; ++i)                             // join
         if (int rc = edge(e->pipe_streams[i], origin)) return rc;
     advance_header_kernel<<<1, 1, 0, origin>>>(state, K);                // pos += K, ncalls += 1: after every hop of the group
     CK(cudaGetLastError());
     return 0;
+}
+
+// kernel nodes of a captured graph (for the launch counter)
+static int count_kernel_nodes(cudaGraph_t graph) {
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) return 0;
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) return 0;
+    int k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++k;
+    }
+    return k;
 }
 
 // K chained one-frame calls as one pipelined graph (cached on the argument set + K)
@@ -583,6 +642,7 @@ static int run_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t st
         if (e->graphs.size() >= 32) {
             for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
             e->graphs.clear();
+            e->graph_kernels.clear();
         }
         cudaStream_t origin = e->pipe_streams[0];
         CK(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
@@ -591,19 +651,38 @@ static int run_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t st
         const cudaError_t ce = cudaStreamEndCapture(origin, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return fail(3, std::string("cudaStreamEndCapture (pipeline): ") + cudaGetErrorString(ce));
+        if (getenv("L2H_GRAPH_STATS")) {            // debug: node / edge census of the captured pipeline graph
+            size_t n_nodes = 0, n_edges = 0;
+            cudaGraphGetNodes(graph, nullptr, &n_nodes);
+            cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &n_edges);
+            std::vector<cudaGraphNode_t> from(n_edges), to(n_edges);
+            std::vector<cudaGraphEdgeData> ed(n_edges);
+            cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &n_edges);
+            size_t prog = 0;
+            for (const auto& d : ed) prog += (d.type == cudaGraphDependencyTypeProgrammatic) ? 1 : 0;
+            fprintf(stderr, "[l2h] pipeline graph: hops %d, nodes %zu, edges %zu, programmatic edges %zu\n", K, n_nodes, n_edges, prog);
+        }
         cudaGraphExec_t exec = nullptr;
+        const int nk = count_kernel_nodes(graph);
         CK(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
+        e->graph_kernels[exec] = nk;
         it = e->graphs.emplace(key, exec).first;
     }
     CK(cudaGraphLaunch(it->second, st));
+    e->launch_count += e->graph_kernels[it->second];
     return 0;
 }
 
 // Launch the chain directly, or replay it from a cached CUDA graph (captured on a private
 // stream the first time this exact argument set is seen; graph launches go to the caller's stream).
 static int run_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st, bool use_graph) {
-    if (!use_graph || (a.flags & L2H_FLAG_TAPS)) return enqueue_chain(e, a, st);
+    if (!use_graph || (a.flags & L2H_FLAG_TAPS)) {
+        int32_t n = 0;
+        l2h_sep_launches_per_forward(e, a.T, &n);
+        e->launch_count += n;
+        return enqueue_chain(e, a, st);
+    }
     std::vector<int64_t> key = {(int64_t)a.x, a.xbs, a.xcs, a.x_len, (int64_t)a.emb, (int64_t)a.state, (int64_t)a.y,
                                 a.ybs, a.ycs, a.y_len, a.B, a.T, (int64_t)a.wsp, (int64_t)a.flags, a.pos_rel};
     auto it = e->graphs.find(key);
@@ -614,6 +693,7 @@ static int run_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st, bool use
         if (e->graphs.size() >= 32) {
             for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
             e->graphs.clear();
+            e->graph_kernels.clear();
         }
         CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue_chain(e, a, e->cap_stream);
@@ -622,11 +702,14 @@ static int run_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st, bool use
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return fail(3, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
         cudaGraphExec_t exec = nullptr;
+        const int nk = count_kernel_nodes(graph);
         CK(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
+        e->graph_kernels[exec] = nk;
         it = e->graphs.emplace(key, exec).first;
     }
     CK(cudaGraphLaunch(it->second, st));
+    e->launch_count += e->graph_kernels[it->second];
     return 0;
 }
 
@@ -749,6 +832,7 @@ int l2h_sep_state_init(void* handle, void* state, int32_t batch, void* stream) {
     const int64_t total = sizeof(StateHeader) / 4 + (int64_t)batch * ss;
     state_init_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(state), total, ss, batch);
     CK(cudaGetLastError());
+    e->launch_count += 1;
     return 0;
 }
 
@@ -774,6 +858,14 @@ int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     // through the pipelined graph, where the mid section is three kernels (mid_a | mid_b | mid_c) -> 8 per block
     const int one_hop = e->use_mid ? ((e->use_pipe && e->pipe_split_mid) ? 8 : 6) : 9;
     *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
+    return 0;
+}
+
+int l2h_sep_launch_count(void* handle, int64_t* kernels, int32_t reset) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    if (kernels) *kernels = e->launch_count;
+    if (reset) e->launch_count = 0;
     return 0;
 }
 
@@ -834,6 +926,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     set_clip_base_kernel<<<1, 1, 0, st>>>(static_cast<float*>(state));
     CK(cudaGetLastError());
+    e->launch_count += 1;
     ChainArgs a{x_dev, (int64_t)NMIC * x_len, x_len, x_len, emb, static_cast<float*>(state), y_dev,
                 (int64_t)NSRC * y_len, y_len, y_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 1};
     if (cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1) {
@@ -872,17 +965,19 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     const std::string n(name);
     if (n == "defaults") {                      // lane counts and mid split back to the built-in defaults
         const SepEngine d{};
-        e->pipe_alanes = d.pipe_alanes; e->pipe_qlanes = d.pipe_qlanes; e->pipe_tlanes = d.pipe_tlanes;
+        e->pipe_alanes = d.pipe_alanes; e->pipe_qlanes = d.pipe_qlanes; e->pipe_clanes = d.pipe_clanes; e->pipe_tlanes = d.pipe_tlanes;
         e->pipe_olanes = d.pipe_olanes; e->pipe_flanes = d.pipe_flanes; e->pipe_blanes = d.pipe_blanes;
-        e->pipe_split_mid = d.pipe_split_mid; e->pipe_frames = d.pipe_frames; e->pipe_skip = 0; e->pipe_pdl = d.pipe_pdl;
+        e->pipe_split_mid = d.pipe_split_mid; e->pipe_frames = d.pipe_frames; e->pipe_skip = 0; e->pipe_pdl = d.pipe_pdl; e->pipe_midb_hops = d.pipe_midb_hops;
     }
     else if (n == "pipeline") e->use_pipe = value != 0;
     else if (n == "pipeline_frames") e->pipe_frames = std::max(2, std::min(PIPE_MAX_FRAMES, (int)value));
     else if (n == "pipeline_lanes") e->pipe_alanes = std::max(1, std::min(PIPE_LANES, (int)value));
     else if (n == "pipeline_debug_skip") e->pipe_skip = value;
     else if (n == "pipeline_pdl") e->pipe_pdl = value;
+    else if (n == "pipeline_midb_hops") e->pipe_midb_hops = std::max(1, std::min(PIPE_MIDB_MAX, (int)value));
     else if (n == "pipeline_split_mid") e->pipe_split_mid = value != 0;
     else if (n == "pipeline_qkv_lanes") e->pipe_qlanes = std::max(1, std::min(PIPE_QLANES, (int)value));
+    else if (n == "pipeline_midc_lanes") e->pipe_clanes = std::max(1, std::min(PIPE_CLANES, (int)value));
     else if (n == "pipeline_attn_lanes") e->pipe_tlanes = std::max(1, std::min(PIPE_TLANES, (int)value));
     else if (n == "pipeline_out_lanes") e->pipe_olanes = std::max(1, std::min(PIPE_OLANES, (int)value));
     else if (n == "pipeline_front_lanes") e->pipe_flanes = std::max(1, std::min(PIPE_FLANES, (int)value));
@@ -892,6 +987,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else return fail(2, "unknown option: " + n);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting
     e->graphs.clear();
+    e->graph_kernels.clear();
     return 0;
 }
 

@@ -39,13 +39,19 @@ def run(mask):
     return 1e3 * best / 500
 
 
+ALL = 1023
+bits = {n: 1 << i for i, n in enumerate(STAGES)}
 base = run(0)
-print(json.dumps({"lanes": combo, "skipped": "none", "us_per_hop": round(base, 2)}), flush=True)
+print(json.dumps({"lanes": combo, "launched": "all", "us_per_hop": round(base, 2)}), flush=True)
 for i, s in enumerate(STAGES):
     t = run(1 << i)
     print(json.dumps({"skipped": s, "us_per_hop": round(t, 2), "gain_us": round(base - t, 2)}), flush=True)
-for label, mask in (("all but lstm", 1023 & ~4), ("all but mid_b", 1023 & ~16), ("all but attn", 1023 & ~128),
-                    ("all but gemm_ih", 1023 & ~2), ("lstm+gemm_ih", 6), ("attn+qkv+attn_out", 64 + 128 + 256), ("everything", 1023)):
-    t = run(mask)
-    print(json.dumps({"skipped": label, "us_per_hop": round(t, 2)}), flush=True)
+groups = [("front",), ("gemm_ih", "lstm", "mid_a"), ("mid_b",), ("mid_c", "qkv"), ("attn",), ("attn_out",), ("back",)]
+for g in groups:                                   # one stage group alone: its own floor
+    keep = sum(bits[n] for n in g)
+    print(json.dumps({"only": "+".join(g), "us_per_hop": round(run(ALL & ~keep), 2)}), flush=True)
+keep = 0
+for g in groups:                                   # cumulative: where does the time appear?
+    keep |= sum(bits[n] for n in g)
+    print(json.dumps({"cumulative_up_to": "+".join(g), "us_per_hop": round(run(ALL & ~keep), 2)}), flush=True)
 net.set_option("pipeline_debug_skip", 0)
