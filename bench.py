@@ -282,8 +282,10 @@ def main():
     clocks = sampler.result()
 
     tm = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    nl = torch.tensor([n_launched.value], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)             # kernels of the whole job
     dev_ms, e2e_ms = float(tm[0]), float(tm[1])
     frames_total = world * FRAMES * args.steps
     value = frames_total / (dev_ms * 1e-3)
@@ -414,7 +416,7 @@ def main():
                     "api": "l2h_sep_stream_host: pinned host clip in, pinned host clip out; per round one cudaMemcpy2DAsync "
                            "H2D of the round's samples, the one-hop kernel chains of the round, one D2H of its output -- all "
                            "inside the timed region, fresh state per step"},
-            "gpu_launches": int(n_launched.value),
+            "gpu_launches": int(nl.item()),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "wall_s": t_wall,
         }
         out.update(extras)

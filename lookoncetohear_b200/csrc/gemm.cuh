@@ -9,6 +9,7 @@
 // Optional prologue: LayerNorm over the K==64 channels of each row (nn.LayerNorm semantics:
 // biased variance, eps inside the sqrt).  Epilogues: bias | bias+PReLU | bias+residual.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -320,9 +321,16 @@ inline cudaError_t launch_rows_gemm_big(const GemmArgs& g, cudaStream_t st, bool
     const size_t smem = ((size_t)g.K * BN + (size_t)GK * (128 + 4)) * sizeof(float);
     const int n_row_tiles = (g.M + 127) / 128;
     const int col_tiles = g.N / BN;
-    const int per_sm = (smem <= 72 * 1024) ? 3 : (smem <= 110 * 1024 ? 2 : 1);
-    int gx = (148 * per_sm + col_tiles - 1) / col_tiles;
+    // resident CTAs per SM: the 128-column variant holds 105 registers x 256 threads -> two; the 64-column variant
+    // three (as far as shared memory allows).  The grid must not exceed what is resident (a second wave of a
+    // persistent kernel doubles its time: ncu, profiles/r01f_ncu_batch256.md), and the row tiles are dealt out
+    // evenly: every CTA takes ceil(tiles / gx_max) of them.
+    const int by_smem = (smem <= 72 * 1024) ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    const int per_sm = std::min(by_smem, BN == 128 ? 2 : 3);
+    int gx = std::max(1, (148 * per_sm) / col_tiles);
     if (gx > n_row_tiles) gx = n_row_tiles;
+    const int per_cta = (n_row_tiles + gx - 1) / gx;
+    gx = (n_row_tiles + per_cta - 1) / per_cta;
     return launch_k(pdl, rows_gemm_big_kernel<BN>, dim3(gx, col_tiles), dim3(256), smem, st, g, n_row_tiles);
 }
 

@@ -14,7 +14,7 @@
 // LDS costs one shared-memory wavefront per 4 B per lane whatever its width (profiles/r01c_lstm_microbench.txt),
 // so a warp computing R rows x C columns per lane gets 32 R C / (R + C) FMAs per wavefront: v1 (C = 1,
 // R = 2 or 8) was bound by the shared-memory pipe at 12 k wavefronts and 9.7 us per tile (ncu,
-// profiles/r01e_ncu_batch256.md).  v2 splits K across KQ adjacent lanes instead of giving every lane its own
+// profiles/r01f_ncu_batch256.md).  v2 splits K across KQ adjacent lanes instead of giving every lane its own
 // column: a lane accumulates 8 rows x C = 4 or 8 columns over K/KQ values of k, the KQ partial tiles are
 // summed by a shuffle reduce-scatter, and every lane ends up owning 8 C / KQ finished outputs for the
 // epilogue.  Weights and activations are stored in k-slices padded by 4 floats so that the 8 lanes of a

@@ -76,6 +76,7 @@ struct SepEngine {
     int pipe_flanes = 4;     // front_kernel hops in flight (<= PIPE_FLANES)
     int pipe_blanes = 4;     // back_kernel hops in flight (<= PIPE_BLANES)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
+    bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
 };
@@ -258,6 +259,14 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     return ws;
 }
 
+// grids of the mid-section kernels: persistent over (stream, row tile) items, as many CTAs per SM as their shared memory
+// allows (fused 225 KB -> 1, mid_a 107 KB -> 2, mid_b 68 KB -> 3, mid_c 50 KB -> 4)
+static inline int mid_items(int B) { return B * ((NF + MID_RT - 1) / MID_RT); }
+static inline dim3 mid_grid_for(int B, int ctas_per_sm) { return dim3(std::min(148 * ctas_per_sm, mid_items(B))); }
+// many streams: the section is throughput-bound and one fused CTA per SM (8 warps) cannot hide its own latencies; the
+// three smaller kernels run 2-4 CTAs per SM (same arithmetic, +3 small global round trips)
+static inline bool mid_split_for_throughput(int B) { return mid_items(B) > 148; }
+
 static bool g_attr_done = false;
 static int set_attrs() {
     if (g_attr_done) return 0;
@@ -347,9 +356,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         l.ndir = 2;
         CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_intra");
-        if (fused_mid) {
-            CK(launch_k(pdl, mid_kernel, dim3(std::min(148, B * ((NF + MID_RT - 1) / MID_RT))), dim3(256), MID_SMEM, st,
-                        (const float*)Y, X, QKVRAW, state, ss, b, W, B));
+        if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
+            float* GI = GX; float* HN = GX + rows * 256;         // the BiLSTM is done with GX
+            CK(launch_k(pdl, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st, (const float*)Y, X, GI, W, B));
+            CK(launch_k(pdl, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, st, (const float*)GI, HN, (int64_t)0, 1, state, ss, b, W, B));
+            CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B));
+            MARK("mid");
+        } else if (fused_mid) {
+            CK(launch_k(pdl, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
             MARK("mid");
         } else {
         g = GemmArgs{};
@@ -457,7 +471,8 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     // serial stage (mid_b -> mid_b of the next hop): everywhere, the parked dependents hold shared memory and CTA
     // slots the running kernels need (measured 14.0 vs 9.4 us per hop, profiles/r01f_pipeline_sweeps.jsonl)
     const int ppdl = e->pipe_pdl;         // stage bit mask (same bits as pipe_skip)
-    const bool split_mid = e->pipe_split_mid && B * ((NF + MID_RT - 1) / MID_RT) <= 148;   // many streams: throughput, not latency
+    const bool many = mid_split_for_throughput(B);
+    const bool split_mid = many ? e->mid_split_large : e->pipe_split_mid;
     float* state = a.state;
     for (int i = 0; i < PIPE_STREAMS; ++i)
         if (!e->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&e->pipe_streams[i], cudaStreamNonBlocking));
@@ -508,8 +523,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     // The serial stage (mid_b) takes `mb` consecutive hops per launch: its ~3 us of launch overhead and its 64 KB of
     // weights are paid once per batch, h stays in shared memory and c in registers from hop to hop.  A batch waits
     // for stage A of all its hops; the upstream block is that far ahead anyway once the pipeline is full.
-    const int mb = split_mid ? std::max(1, std::min(e->pipe_midb_hops, PIPE_MIDB_MAX)) : 1;
-    const dim3 mid_grid(std::min(148, B * ((NF + MID_RT - 1) / MID_RT)));
+    const int mb = (split_mid && !many) ? std::max(1, std::min(e->pipe_midb_hops, PIPE_MIDB_MAX)) : 1;
     float* PRE = a.wsp + ws.PRE;                                       // speaker-gate scratch: front stream only
     for (int k0 = 0; k0 < K; k0 += mb) {
         const int k1 = std::min(K, k0 + mb);                           // this batch: hops [k0, k1)
@@ -541,7 +555,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 // only the W_hh product + cell (mid_b) is serial per block; the rest rides on the parallel lanes.
                 // GI / H' live in the hop's GX slot, which the BiLSTM has finished with.
                 if (split_mid && !(e->pipe_skip & 8))
-                    CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid, dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GX, W, B));
+                    CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GX, W, B));
                 if (int rc = record(&a_done[b][k], st_a)) return rc;
             }
             // ---- the serial stage: one launch for the batch ----------------------------------------------------
@@ -551,10 +565,10 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 float* GI = wsp + ws.GX; float* HN = GI + (int64_t)rows * 256;
                 if (split_mid) {
                     if (!(e->pipe_skip & 16))
-                        CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid, dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, slot,
+                        CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, slot,
                                     k1 - k0, state, ss, b, W, B));
                 } else if (!(e->pipe_skip & 16)) {
-                    CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid, dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y), wsp + ws.X,
+                    CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y), wsp + ws.X,
                                 wsp + ws.QKVRAW, state, ss, b, W, B));
                 }
             }
@@ -570,7 +584,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                     cudaStream_t st_c = sBc(b, k);
                     CK(cudaStreamWaitEvent(st_c, midb_done, 0));
                     if (!(e->pipe_skip & 32))
-                        CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid, dim3(256), MID_C_SMEM, st_c, (const float*)HN, X, QKVRAW, W, B));
+                        CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st_c, (const float*)HN, X, QKVRAW, W, B));
                     if (int rc = edge(st_c, st_q)) return rc;
                 } else {
                     CK(cudaStreamWaitEvent(st_q, midb_done, 0));
@@ -984,6 +998,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "pipeline_back_lanes") e->pipe_blanes = std::max(1, std::min(PIPE_BLANES, (int)value));
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
+    else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else return fail(2, "unknown option: " + n);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting
     e->graphs.clear();
