@@ -125,7 +125,16 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
  * number of one-hop calls a pipelined graph holds (1 = pipelining off) */
 int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_per_call, size_t* bytes);
 int l2h_sep_pipeline_frames(void* handle, int32_t* frames);
-/* runtime switches (also env L2H_PIPE / L2H_PDL / L2H_MID at create): "pipeline", "pdl", "fused_mid" = 0 | 1 */
+/* runtime switches (also env L2H_PIPE / L2H_PDL / L2H_MID at create).  0 | 1: "pipeline" (wavefront graph for streams of
+ * one-hop calls), "pdl", "fused_mid", "pipeline_split_mid" (mid section as mid_a | mid_b | mid_c in the graph),
+ * "mid_split_large" (the same three kernels for many streams).  Counts: "pipeline_frames" (hops per graph, <= 250),
+ * "pipeline_midb_hops" (hops per launch of the serial stage, <= 8) and the hops in flight per stage: "pipeline_lanes"
+ * (BiLSTM, <= 12), "pipeline_midc_lanes" (<= 3), "pipeline_qkv_lanes" (<= 3), "pipeline_attn_lanes" (<= 4),
+ * "pipeline_out_lanes" (<= 4), "pipeline_front_lanes" (<= 4), "pipeline_back_lanes" (<= 6).  Bit masks over the stages
+ * front=1, W_ih gemm=2, bilstm=4, mid_a=8, mid_b=16, mid_c=32, qkv=64, attention=128, attn_out=256, back=512:
+ * "pipeline_pdl" (stages launched with programmatic dependent launch; default 16) and "pipeline_debug_skip" (stages NOT
+ * launched -- timing experiments only, the output is garbage).  "defaults" restores all pipeline settings.  Results do
+ * not depend on any of them (bit-identical, tests/test_sep_gpu.py). */
 int l2h_sep_set_option(void* handle, const char* name, int32_t value);
 
 /* where the tap area starts inside the workspace (floats) and its stage count; stage s holds
@@ -141,7 +150,8 @@ int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float
                     int32_t iters, const char** names, float* ms_total, int32_t* counts, int32_t* n_names,
                     void* stream);
 
-/* number of kernels one l2h_sep_forward launches (for bench.py's gpu_launches) */
+/* number of kernels one l2h_sep_forward of `frames` hops launches at a few streams (see l2h_sep_launch_count for the
+   exact count of everything a handle launched, pipelined streams included) */
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);
 
 /* kernels this handle has launched so far (a CUDA-graph replay counts its kernel nodes); reset != 0 zeroes the

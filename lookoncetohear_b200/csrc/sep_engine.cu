@@ -868,9 +868,10 @@ int l2h_sep_tap_info(void* handle, int32_t batch, int32_t frames, int64_t* off, 
 int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !n) return fail(1, "bad argument");
-    // one-hop calls: 6 kernels per block fused (gemm, bilstm, mid, qkv, attn, attn_out); streams of one-hop calls run
-    // through the pipelined graph, where the mid section is three kernels (mid_a | mid_b | mid_c) -> 8 per block
-    const int one_hop = e->use_mid ? ((e->use_pipe && e->pipe_split_mid) ? 8 : 6) : 9;
+    // one l2h_sep_forward: a one-hop call is 6 kernels per block (gemm, bilstm, mid, qkv, attn, attn_out; 8 with many
+    // streams, where the mid section runs as three kernels), a multi-hop call 10.  Streams of one-hop calls go through
+    // the pipelined graph instead -- l2h_sep_launch_count has the exact figure for everything this handle launched.
+    const int one_hop = e->use_mid ? 6 : 9;
     *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
     return 0;
 }

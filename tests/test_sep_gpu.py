@@ -259,3 +259,28 @@ def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
     assert torch.equal(st_pipe["deconv_buf"], st_seq["deconv_buf"])
     y_ref = rs.sep_forward(sd, x[:1, :, :128 * 64], e[:1])
     _check(y_pipe[:1, :, :128 * 64], y_ref)
+
+
+def test_launch_counter_counts_graph_nodes(model, dev):
+    """bench.py's gpu_launches comes from l2h_sep_launch_count: a replayed CUDA graph counts its kernel nodes.  One
+    sequential hop = 1 front + 3 x 6 + 1 back = 20 kernels; a pipelined 8-hop stream = 8 x 23 + one mid_b launch per block
+    and 4 hops + the header advance + the clip-base kernel."""
+    import ctypes
+    from lookoncetohear_b200 import _cabi
+    net, _ = model
+    L = _cabi.lib()
+    x, _ = synth.mixture(1, 128 * 8, seed0=5)
+    e = synth.embedding(1, seed0=6)[:, 0].to(dev)
+    xd = F.pad(x, (0, 64)).to(dev)
+    st = net.init_buffers(1, dev)
+    n = ctypes.c_int64()
+    _cabi.check(L.l2h_sep_launch_count(net._engine(), None, 1))
+    net.predict(xd[..., :192], e, st, pad=False)
+    _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
+    assert n.value == 20
+    st = net.init_buffers(1, dev)
+    _cabi.check(L.l2h_sep_launch_count(net._engine(), None, 1))
+    net.stream_dev(x.to(dev), e, chunks_per_call=1, state=st, n_calls=8)
+    torch.cuda.synchronize()
+    _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
+    assert n.value == 8 * 23 + 3 * 2 + 1 + 1
