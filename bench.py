@@ -307,12 +307,18 @@ def main():
         lat = []
         net.stream_dev(x_dev, emb, chunks_per_call=1, state=st, n_calls=60, out=y_dev)
         torch.cuda.synchronize()
+        lat_dev = []
         for i in range(200):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
+            ea.record()
             net.stream_dev(x_dev[..., :HOP * 8], emb, chunks_per_call=1, state=st, n_calls=1, out=y_dev[..., :HOP * 8])
+            eb.record()
             torch.cuda.synchronize()
             lat.append(time.perf_counter() - t0)
-        extras["chunk_latency_us"] = 1e6 * statistics.median(lat)
+            lat_dev.append(ea.elapsed_time(eb))
+        extras["chunk_latency_us"] = 1e6 * statistics.median(lat)          # host wall clock: call + graph launch + sync
+        extras["chunk_latency_device_us"] = 1e3 * statistics.median(lat_dev)   # CUDA events around the same call
         # the same 500-hop stream with the hops run strictly one after the other (no wavefront pipelining)
         net.set_option("pipeline", 0)
         for it in range(3):

@@ -63,7 +63,7 @@ struct SepEngine {
     std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
     cudaStream_t pipe_streams[96] = {};
     std::vector<cudaEvent_t> pipe_events;
-    int pipe_frames = 250;   // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES)
+    int pipe_frames = 0;     // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES); 0 = auto: as many as a 24 GB workspace holds
     int pipe_alanes = 12;    // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
     int pipe_midb_hops = 4;       // pipeline: consecutive hops one mid_b launch takes (<= PIPE_MIDB_MAX)
     int pipe_skip = 0;            // DEBUG (timing experiments only): bit mask of pipeline stages NOT to launch
@@ -440,7 +440,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // workspace slot; state addressing uses pos + frame_k / parity(ncalls + frame_k); the header advances once,
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
-constexpr int PIPE_MAX_FRAMES = 250;
+constexpr int PIPE_MAX_FRAMES = 500;
 constexpr int PIPE_LANES = 12;     // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
 constexpr int PIPE_FLANES = 4;     // max front_kernel lanes (frames of a group do not depend on each other there)
 constexpr int PIPE_BLANES = 6;     // max back_kernel lanes
@@ -456,6 +456,14 @@ constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites 
 static_assert(PIPE_STREAMS <= 96, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
+// hops per pipelined graph: fill + drain cost one chain latency (~0.25 ms) per graph, so as many as possible -- every hop
+// in flight owns a workspace slot (350 KB per stream), which is what bounds it for many streams
+static int pipe_frames_for(SepEngine* e, int B) {
+    if (e->pipe_frames > 0) return e->pipe_frames;
+    const int64_t budget = (int64_t)24 << 30;
+    const int64_t fit = budget / (pipe_slot_floats(e, B) * (int64_t)sizeof(float));
+    return (int)std::max<int64_t>(2, std::min<int64_t>(PIPE_MAX_FRAMES, fit));
+}
 
 static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t origin) {
     if (e->n_blocks != 3) return fail(1, "pipeline graph is specialised to 3 blocks");
@@ -906,7 +914,7 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
     int group = cpc;
     if (pipe) {
         const int64_t slot = pipe_slot_floats(e, batch);
-        group = (int)std::min<int64_t>(std::min(e->pipe_frames, n_calls), (int64_t)(ws_bytes / sizeof(float)) / slot);
+        group = (int)std::min<int64_t>(std::min(pipe_frames_for(e, batch), n_calls), (int64_t)(ws_bytes / sizeof(float)) / slot);
         if (group < 2) group = 1;
     }
     const int hops_total = n_calls * cpc;
@@ -947,7 +955,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
     if (cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1) {
         // groups of up to PIPE_MAX_FRAMES one-frame calls, each group one wavefront-pipelined graph
         const int64_t slot = pipe_slot_floats(e, batch);
-        int kmax = (int)std::min<int64_t>(e->pipe_frames, (int64_t)(ws_bytes / sizeof(float)) / slot);
+        int kmax = (int)std::min<int64_t>(pipe_frames_for(e, batch), (int64_t)(ws_bytes / sizeof(float)) / slot);
         if (kmax >= 2) {
             int done = 0;
             while (done < n_calls) {
@@ -968,7 +976,7 @@ int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_p
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !bytes || batch <= 0 || chunks_per_call <= 0) return fail(1, "bad argument");
     if (chunks_per_call == 1 && e->use_pipe)
-        *bytes = (size_t)pipe_slot_floats(e, batch) * PIPE_MAX_FRAMES * sizeof(float);
+        *bytes = (size_t)pipe_slot_floats(e, batch) * pipe_frames_for(e, batch) * sizeof(float);
     else
         *bytes = (size_t)carve(e->n_blocks, batch, chunks_per_call, 0).total * sizeof(float);
     return 0;
@@ -985,7 +993,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
         e->pipe_split_mid = d.pipe_split_mid; e->pipe_frames = d.pipe_frames; e->pipe_skip = 0; e->pipe_pdl = d.pipe_pdl; e->pipe_midb_hops = d.pipe_midb_hops;
     }
     else if (n == "pipeline") e->use_pipe = value != 0;
-    else if (n == "pipeline_frames") e->pipe_frames = std::max(2, std::min(PIPE_MAX_FRAMES, (int)value));
+    else if (n == "pipeline_frames") e->pipe_frames = value <= 0 ? 0 : std::max(2, std::min(PIPE_MAX_FRAMES, (int)value));
     else if (n == "pipeline_lanes") e->pipe_alanes = std::max(1, std::min(PIPE_LANES, (int)value));
     else if (n == "pipeline_debug_skip") e->pipe_skip = value;
     else if (n == "pipeline_pdl") e->pipe_pdl = value;
@@ -1010,7 +1018,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
 int l2h_sep_pipeline_frames(void* handle, int32_t* frames) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !frames) return fail(1, "bad argument");
-    *frames = (e->use_pipe && e->use_mid && e->n_blocks == 3) ? PIPE_MAX_FRAMES : 1;
+    *frames = (e->use_pipe && e->use_mid && e->n_blocks == 3) ? pipe_frames_for(e, 1) : 1;
     return 0;
 }
 

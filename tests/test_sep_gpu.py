@@ -234,7 +234,7 @@ PIPE_OPTIONS = ("pipeline_lanes", "pipeline_qkv_lanes", "pipeline_attn_lanes", "
 def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
     """One-hop calls captured as a (block, hop) wavefront graph must reproduce the strictly sequential
     hop-by-hop run bit for bit (same arithmetic, only the schedule and the kernel boundaries of the mid
-    section differ), across a group boundary (230 hops = 100 + 100 + 30), for several streams and for
+    section differ), within one graph and across group boundaries (230 hops = 100 + 100 + 30), for several streams and for
     several lane counts per stage (every lane count exercises other event edges); both match the oracle."""
     net, sd = model
     T, B = 230, 3
@@ -243,6 +243,7 @@ def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
     xd, ed = x.to(dev), e[:, 0].to(dev)
     try:
         if lanes is not None:
+            net.set_option("pipeline_frames", 100)        # 230 hops = 100 + 100 + 30; the default takes them as one graph
             for n, v in zip(PIPE_OPTIONS, lanes):
                 net.set_option(n, v)
         net.set_option("pipeline", 1)
