@@ -158,6 +158,15 @@ int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n);
    counter after reading.  bench.py's gpu_launches is read from here around the timed region. */
 int l2h_sep_launch_count(void* handle, int64_t* kernels, int32_t reset);
 
+/* diagnostics: device-side timeline of the separator's kernels.  l2h_sep_trace_start(handle, capacity) allocates a buffer
+   of `capacity` records and switches tracing on (capacity 0: off); from then on thread 0 of the first CTA of every
+   instrumented kernel stores one 32-byte record {u64 t0_ns, u64 t1_ns (globaltimer at entry / exit), u64 activation
+   pointer, u32 kernel id (0 front, 1 W_ih gemm, 2 bilstm, 3 mid_a, 4 mid_b, 5 mid_c, 6 qkv, 7 attention, 8 attn_out,
+   9 back, 10 fused mid), u32 SM}.  l2h_sep_trace_read synchronises, copies up to max_records of them to the host and
+   restarts the trace.  Used by tools/pipe_trace.py; costs one atomic per kernel while on, one load while off. */
+int l2h_sep_trace_start(void* handle, int32_t capacity);
+int l2h_sep_trace_read(void* handle, void* records_host, int32_t max_records, int32_t* n_records);
+
 /* ---- enrollment network (EmbedTFGridNet, configs/embed.json:5-10) ---------------------------- */
 typedef struct l2h_embed_config {
     int32_t embed_dim;  /* 256 */

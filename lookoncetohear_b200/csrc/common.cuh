@@ -115,6 +115,40 @@ L2H_DEVINL void griddep_launch() { asm volatile("griddepcontrol.launch_dependent
 
 #include <utility>
 namespace l2h {
+
+// ---- pipeline tracing (diagnostics; off unless the host sets g_trace) ---------------------------------------
+// Thread 0 of CTA (0,0,0) of an instrumented kernel records %globaltimer at entry and at exit, the SM it ran on, a
+// kernel id and the low bits of one activation pointer (every hop owns a workspace slot, so the pointer says which
+// hop the launch belongs to).  tools/pipe_trace.py turns the records into a per-stage timeline of the pipelined graph.
+struct TraceRec { unsigned long long t0, t1; unsigned long long ptr; unsigned int kernel, sm; };
+static __device__ TraceRec* g_trace = nullptr;
+static __device__ unsigned int g_trace_cap = 0;
+static __device__ unsigned int g_trace_n = 0;
+enum TraceKernel { TK_FRONT = 0, TK_GEMM, TK_LSTM, TK_MID_A, TK_MID_B, TK_MID_C, TK_QKV, TK_ATTN, TK_ATTN_OUT, TK_BACK, TK_MID };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct TraceScope {
+    TraceRec* rec;
+    __device__ __forceinline__ TraceScope(int kernel, const void* ptr) : rec(nullptr) {
+        if ((threadIdx.x | blockIdx.x | blockIdx.y | blockIdx.z) == 0 && g_trace != nullptr) {
+            const unsigned int slot = atomicAdd(&g_trace_n, 1u);
+            if (slot < g_trace_cap) {
+                rec = g_trace + slot;
+                unsigned int sm;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+                rec->ptr = (unsigned long long)ptr; rec->kernel = (unsigned int)kernel; rec->sm = sm; rec->t1 = 0;
+                rec->t0 = globaltimer_ns();
+            }
+        }
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if (rec != nullptr) rec->t1 = globaltimer_ns();
+    }
+};
+
 // host: launch with (or without) the PDL attribute
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

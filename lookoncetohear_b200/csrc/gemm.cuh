@@ -47,6 +47,7 @@ rows_gemm_kernel(const GemmArgs g) {
     float* As = smem;                      // [GK][BM + APAD]  (transposed: k-major)
     float* Bs = smem + GK * (BM + APAD);   // [GK][BN]
 
+    TraceScope trace_(TK_GEMM, g.A);
     griddep_launch();
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;

@@ -318,6 +318,7 @@ lstm_rec3_kernel(const LstmArgs a) {
     __shared__ __align__(16) float gring[PRE ? 1 : L3_STAGES][PRE ? 1 : NSEQ][PRE ? 4 : 256];
     __shared__ __align__(8) unsigned long long gbar;
 
+    TraceScope trace_(TK_LSTM, a.gx);
     griddep_launch();
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;

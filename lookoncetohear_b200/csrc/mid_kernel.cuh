@@ -123,6 +123,7 @@ mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict
     float* x1s = A6 + MID_A6;             // [RT][64] X1 (LayerNorm input)
 
     __shared__ __align__(8) unsigned long long wbar;
+    TraceScope trace_(TK_MID, Y);
     griddep_launch();
     const int tid = threadIdx.x;
     constexpr int TILES = (NF + MID_RT - 1) / MID_RT;       // row tiles per stream
@@ -249,6 +250,7 @@ mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restri
     float* A3 = A1 + MID_A1;                          // LN(X1), k-sliced
     float* x1s = A3 + MID_A3;
     __shared__ __align__(8) unsigned long long wbar;
+    TraceScope trace_(TK_MID_A, Y);
     griddep_launch();
     const int tid = threadIdx.x;
     constexpr int TILES = (NF + MID_RT - 1) / MID_RT;
@@ -319,6 +321,7 @@ mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, int64_t hop_s
     float* W3b = sm;                                  // W_hh, k-sliced
     float* A3 = W3b + (MID_W5 - MID_W3B);             // h, k-sliced
     __shared__ __align__(8) unsigned long long wbar;
+    TraceScope trace_(TK_MID_B, GI);
     griddep_launch();
     const int tid = threadIdx.x;
     constexpr int TILES = (NF + MID_RT - 1) / MID_RT;
@@ -390,6 +393,7 @@ mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restr
     float* A5 = W5 + (MID_PACK - MID_W5);
     float* A6 = A5 + MID_A5;
     __shared__ __align__(8) unsigned long long wbar;
+    TraceScope trace_(TK_MID_C, Hn);
     griddep_launch();
     const int tid = threadIdx.x;
     constexpr int TILES = (NF + MID_RT - 1) / MID_RT;

@@ -57,11 +57,13 @@ struct SepEngine {
     // launch-bound unless replayed as a graph)
     std::map<std::vector<int64_t>, cudaGraphExec_t> graphs;
     std::map<cudaGraphExec_t, int> graph_kernels;   // kernel nodes per cached graph
+    TraceRec* trace_dev = nullptr;                  // device trace buffer (l2h_sep_trace_start)
+    int trace_cap = 0;
     int64_t launch_count = 0;                       // kernels launched so far (graph replays counted by their kernel nodes)
     cudaStream_t cap_stream = nullptr;
     struct MidSrc { int64_t wl1, wih2, whh2t, wl2, wqkv, dst; };
     std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
-    cudaStream_t pipe_streams[96] = {};
+    cudaStream_t pipe_streams[128] = {};
     std::vector<cudaEvent_t> pipe_events;
     int pipe_frames = 0;     // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES); 0 = auto: as many as a 24 GB workspace holds
     int pipe_alanes = 12;    // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
@@ -73,8 +75,8 @@ struct SepEngine {
     int pipe_clanes = 2;     // mid_c hops in flight per block (<= PIPE_CLANES)
     int pipe_tlanes = 3;     // attention hops in flight per block (<= PIPE_TLANES)
     int pipe_olanes = 4;     // attn_out hops in flight per block (<= PIPE_OLANES)
-    int pipe_flanes = 4;     // front_kernel hops in flight (<= PIPE_FLANES)
-    int pipe_blanes = 4;     // back_kernel hops in flight (<= PIPE_BLANES)
+    int pipe_flanes = 6;     // front_kernel hops in flight (<= PIPE_FLANES)
+    int pipe_blanes = 6;     // back_kernel hops in flight (<= PIPE_BLANES)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
@@ -441,11 +443,11 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
 // at the last hop of the graph.  The arithmetic and its order per stream are unchanged: results are
 // bit-identical to running the hops one after the other (tests/test_sep_gpu.py).
 constexpr int PIPE_MAX_FRAMES = 500;
-constexpr int PIPE_LANES = 12;     // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
-constexpr int PIPE_FLANES = 4;     // max front_kernel lanes (frames of a group do not depend on each other there)
+constexpr int PIPE_LANES = 16;     // max hops of stage A (BiLSTM) in flight per block (engine->pipe_alanes used)
+constexpr int PIPE_FLANES = 8;     // max front_kernel lanes (frames of a group do not depend on each other there)
 constexpr int PIPE_BLANES = 6;     // max back_kernel lanes
 constexpr int PIPE_BASE = 1 + PIPE_FLANES + PIPE_BLANES;
-constexpr int PIPE_QLANES = 3;     // max qkv lanes (hops write different ring rows; RING - ATT = 2 may run ahead of the attention)
+constexpr int PIPE_QLANES = 4;     // max qkv lanes (hops write different ring rows; RING - ATT = 6 may run ahead of the attention)
 constexpr int PIPE_CLANES = 3;     // max mid_c lanes (no hop-to-hop dependency, not bound by the ring guard)
 constexpr int PIPE_TLANES = 4;     // max attention lanes (attention only reads the rings)
 constexpr int PIPE_OLANES = 4;     // max attn_out lanes (no hop-to-hop dependency)
@@ -453,7 +455,7 @@ constexpr int PIPE_PER_BLOCK = PIPE_LANES + 1 + PIPE_QLANES + PIPE_TLANES + PIPE
 constexpr int PIPE_STREAMS = PIPE_BASE + 3 * PIPE_PER_BLOCK;
 constexpr int PIPE_MIDB_MAX = 8;   // max hops per mid_b launch
 constexpr int PIPE_QKV_AHEAD = RING - ATT;         // qkv of hop t+3 overwrites a ring row hop t's attention still reads
-static_assert(PIPE_STREAMS <= 96, "pipe_streams[]");
+static_assert(PIPE_STREAMS <= 128, "pipe_streams[]");
 
 static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks, B, 1, 0).total; }
 // hops per pipelined graph: fill + drain cost one chain latency (~0.25 ms) per graph, so as many as possible -- every hop
@@ -881,6 +883,40 @@ int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     // the pipelined graph instead -- l2h_sep_launch_count has the exact figure for everything this handle launched.
     const int one_hop = e->use_mid ? 6 : 9;
     *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
+    return 0;
+}
+
+int l2h_sep_trace_start(void* handle, int32_t capacity) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || capacity < 0) return fail(1, "bad argument");
+    CK(cudaDeviceSynchronize());
+    TraceRec* none = nullptr;
+    unsigned int zero = 0;
+    CK(cudaMemcpyToSymbol(g_trace, &none, sizeof(none)));
+    if (e->trace_dev) { cudaFree(e->trace_dev); e->trace_dev = nullptr; e->trace_cap = 0; }
+    if (capacity == 0) return 0;                       // tracing off
+    CK(cudaMalloc(&e->trace_dev, (size_t)capacity * sizeof(TraceRec)));
+    CK(cudaMemset(e->trace_dev, 0, (size_t)capacity * sizeof(TraceRec)));
+    e->trace_cap = capacity;
+    const unsigned int cap = (unsigned int)capacity;
+    CK(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+    CK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+    CK(cudaMemcpyToSymbol(g_trace, &e->trace_dev, sizeof(e->trace_dev)));
+    return 0;
+}
+
+int l2h_sep_trace_read(void* handle, void* records_host, int32_t max_records, int32_t* n_records) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !n_records) return fail(1, "bad argument");
+    CK(cudaDeviceSynchronize());
+    unsigned int n = 0;
+    CK(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
+    n = std::min<unsigned int>(n, (unsigned int)e->trace_cap);
+    *n_records = (int32_t)n;
+    const unsigned int take = std::min<unsigned int>(n, (unsigned int)std::max(0, max_records));
+    if (records_host && take) CK(cudaMemcpy(records_host, e->trace_dev, (size_t)take * sizeof(TraceRec), cudaMemcpyDeviceToHost));
+    unsigned int zero = 0;
+    CK(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));   // the next run starts a fresh trace
     return 0;
 }
 

@@ -92,6 +92,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     __shared__ __align__(16) float xs[NMIC][448];
     __shared__ float U[3][4][100];      // [frame t-2..t][ch][1 + f], zero-padded in f
     __shared__ __align__(8) unsigned long long wbar;
+    TraceScope trace_(TK_FRONT, X);
     griddep_launch();
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     if (t == T) {                      // the extra CTA of this stream: speaker-gate memo
@@ -274,6 +275,7 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
     float* LNP = P + NF * QKV_PLD;       // gq[584] bq[584] gk[584] bk[584] gv[1552] bv[1552]
     __shared__ __align__(8) unsigned long long bars[2];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    TraceScope trace_(TK_QKV, X);
     griddep_launch();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -604,6 +606,7 @@ attn_cluster_kernel(const float* __restrict__ Qbuf, const float* __restrict__ Ka
     __shared__ float ml[2];                        // its running max and sum
     __shared__ float sc[16];
     __shared__ float coef[ATT_CL];
+    TraceScope trace_(TK_ATTN, Qbuf);
     griddep_launch();
     griddep_wait();
     cg::cluster_group cluster = cg::this_cluster();
@@ -735,6 +738,7 @@ attn_out_kernel(const float* __restrict__ Z, float* __restrict__ X, const float*
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     float* xr = X + ((int64_t)b * T + t) * NF * CH;
     const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
+    TraceScope trace_(TK_ATTN_OUT, Z);
     griddep_launch();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -851,6 +855,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     const int t = blockIdx.x / BACK_CL, b = blockIdx.y, tid = threadIdx.x;
     const int f0 = back_f0(part), f1 = back_f0(part + 1), nf = f1 - f0;
     const int ld = nf + 2;                             // staged rows per frame slot: bins f0-1 .. f1
+    TraceScope trace_(TK_BACK, X);
     griddep_launch();
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init();

@@ -19,8 +19,10 @@ constexpr int NHEAD = 4;       // L
 constexpr int QE = 6;          // ceil(512/97)
 constexpr int VD = 16;         // D / heads
 constexpr int ATT = 50;        // local_atten_len
-constexpr int RING = 52;       // K/V ring slots per head: the 50-frame window + 2 spare, so that the ring writes of
-                               // hops t+1, t+2 never touch a row hop t's attention still reads (pipelined streaming)
+constexpr int RING = 56;       // K/V ring slots per head: the 50-frame window + 6 spare, so that the ring writes of
+                               // hops t+1 .. t+6 never touch a row hop t's attention still reads (pipelined streaming;
+                               // with 2 spare rows the qkv -> attention -> qkv(t+3) cycle, 21 us per 3 hops, bound the
+                               // pipeline: profiles/r01f_pipeline_trace.md)
 constexpr int SPK = 256;
 constexpr int QK_DIM = NF * QE;     // 582
 constexpr int QK_LD = 584;          // padded to a multiple of 4 floats (16 B rows)
@@ -50,7 +52,7 @@ constexpr int64_t ST_DECONV = ST_CONV + 2 * 2 * 4 * NF;         // [2][2][97][64
 constexpr int64_t ST_ISTFT = ST_DECONV + 2 * 2 * FC;            // [2][2 ears][194]
 constexpr int64_t ST_BLK = ST_ISTFT + 2 * NSRC * NROW;          // blocks start
 constexpr int64_t BK_K = 0;                                     // ring [4][52][584], slot = frame mod 52
-constexpr int64_t BK_V = BK_K + (int64_t)NHEAD * RING * QK_LD;  // ring [4][52][1552]
+constexpr int64_t BK_V = BK_K + (int64_t)NHEAD * RING * QK_LD;  // ring [4][RING][1552]
 constexpr int64_t BK_H = BK_V + (int64_t)NHEAD * RING * V_DIM;  // [97][64]
 constexpr int64_t BK_C = BK_H + FC;                             // [97][64]
 constexpr int64_t BK_STRIDE = BK_C + FC;

@@ -121,9 +121,9 @@ class SepState(dict):
     _ST_DECONV = _ST_CONV + 2 * 2 * 4 * 97
     _ST_ISTFT = _ST_DECONV + 2 * 2 * 6208
     _ST_BLK = _ST_ISTFT + 2 * 2 * 194
-    _RING = 52                      # K/V ring slots per head (csrc/sep_layout.h)
-    _BK_V = 4 * 52 * 584
-    _BK_H = _BK_V + 4 * 52 * 1552
+    _RING = 56                      # K/V ring slots per head (csrc/sep_layout.h)
+    _BK_V = 4 * _RING * 584
+    _BK_H = _BK_V + 4 * _RING * 1552
     _BK_C = _BK_H + 6208
     _BK_STRIDE = _BK_C + 6208
 
@@ -138,7 +138,7 @@ class SepState(dict):
         out = dict(conv_buf=conv.permute(0, 2, 1, 3).contiguous(),
                    deconv_buf=deconv.permute(0, 3, 1, 2).contiguous(),
                    istft_buf=istft.unsqueeze(-1).contiguous(), gridnet_bufs={})
-        # ring slot of frame n is n % 52; history rows are frames pos-49 .. pos-1
+        # ring slot of frame n is n % RING; history rows are frames pos-49 .. pos-1
         frames = torch.arange(pos - 49, pos)
         slots = torch.remainder(frames, self._RING).to(self.buf.device)
         live = (frames >= 0).to(self.buf.device, self.buf.dtype)[None, None, :, None]

@@ -229,7 +229,7 @@ PIPE_OPTIONS = ("pipeline_lanes", "pipeline_qkv_lanes", "pipeline_attn_lanes", "
                 "pipeline_back_lanes", "pipeline_split_mid", "pipeline_pdl", "pipeline_midb_hops", "pipeline_midc_lanes")
 
 
-@pytest.mark.parametrize("lanes", [None, (12, 3, 4, 4, 4, 6, 1, 1023, 8, 3), (3, 1, 1, 1, 1, 2, 0, 16, 1, 1), (5, 2, 2, 3, 3, 3, 1, 0, 3, 2)],
+@pytest.mark.parametrize("lanes", [None, (16, 4, 4, 4, 8, 6, 1, 1023, 8, 3), (3, 1, 1, 1, 1, 2, 0, 16, 1, 1), (5, 2, 2, 3, 3, 3, 1, 0, 3, 2)],
                          ids=["default", "max-lanes-pdl-everywhere-midb8", "few-lanes-fused-mid", "odd-lanes-no-pdl-midb3"])
 def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
     """One-hop calls captured as a (block, hop) wavefront graph must reproduce the strictly sequential

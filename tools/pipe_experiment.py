@@ -14,7 +14,7 @@ x, _ = synth.mixture(1, 64000)
 x = x.to(dev)
 emb = synth.embedding(1)[:, 0].to(dev)
 y = torch.empty(1, 2, 64000, device=dev)
-combos = sys.argv[1:] or ["12:3:3:4:4:4:1:16:4:2:250", "12:3:3:4:4:4:1:16:4:2:500", "12:3:3:4:4:4:1:16:4:2:0", "12:3:3:4:4:4:1:16:8:2:500", "12:3:3:4:4:4:1:16:2:2:500"]
+combos = sys.argv[1:] or ["12:3:3:4:4:4:1:16:4:2:0", "12:3:3:4:6:6:1:16:4:2:0", "16:3:3:4:6:6:1:16:4:2:0", "16:4:4:4:8:6:1:16:4:3:0", "16:4:4:4:8:6:1:16:8:3:0", "16:3:3:4:6:6:1:16:2:2:0", "14:3:3:4:6:5:1:16:4:2:0"]
 names = ("pipeline_lanes", "pipeline_qkv_lanes", "pipeline_attn_lanes", "pipeline_out_lanes", "pipeline_front_lanes",
          "pipeline_back_lanes", "pipeline_split_mid", "pipeline_pdl", "pipeline_midb_hops", "pipeline_midc_lanes", "pipeline_frames")
 for combo in combos:
