@@ -364,12 +364,13 @@ def main():
                 ms = a.elapsed_time(b)
                 best = ms if best is None else min(best, ms)
             fps = nb * (nsteps - 10) / (best * 1e-3)
+            state_gb = stb.buf.numel() * stb.buf.element_size() / 1e9
             pkb = peaks()
             extras["batched_streaming_256"] = {
                 "streams": nb, "frames_per_s": fps, "rtf_aggregate": fps / 125.0, "ms_per_hop_step": best / (nsteps - 10),
                 "hbm_gbs_algorithmic": fps * BYTES_PER_FRAME / 1e9,
                 "hbm_frac": fps * BYTES_PER_FRAME / 1e9 / pkb["hbm_gbs"], "peak_source": pkb["source"],
-                "note": "state (1.38 GB) >> L2: every hop re-reads each stream's K/V rings from HBM"}
+                "note": "state (%.2f GB) >> L2: every hop re-reads each stream's K/V rings from HBM" % state_gb}
             del xb, yb, stb
         except Exception as exc:                                   # never let an extra break the bench line
             extras["batched_streaming_256"] = {"error": repr(exc)[:200]}
