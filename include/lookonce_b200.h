@@ -74,6 +74,9 @@ int l2h_sep_destroy(void* handle);
 int l2h_sep_load_weight(void* handle, const char* name, const float* host_data, int64_t numel);
 /* number of reference tensors the engine expects / has received so far */
 int l2h_sep_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loaded);
+/* the index-th expected tensor (0 <= index < n_expected, alphabetical): its reference name (owned by the handle) and
+ * element count -- what a host that converts a checkpoint iterates over (examples/stream_clip.cpp) */
+int l2h_sep_weight_info(void* handle, int32_t index, const char** name, int64_t* numel);
 /* upload the staged weights (one H2D of ~8 MB on `stream`, then synchronises it) */
 int l2h_sep_commit_weights(void* handle, void* stream);
 

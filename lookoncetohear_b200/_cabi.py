@@ -69,6 +69,8 @@ _SIGS = {
                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]),
     "l2h_sep_launches_per_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32,
                                                    ctypes.POINTER(ctypes.c_int32)]),
+    "l2h_sep_weight_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p),
+                                          ctypes.POINTER(ctypes.c_int64)]),
     "l2h_sep_launch_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
     "l2h_sep_trace_start": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "l2h_sep_trace_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),

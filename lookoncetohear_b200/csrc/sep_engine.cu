@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <iterator>
 #include <map>
 #include <tuple>
 #include <string>
@@ -797,6 +798,17 @@ int l2h_sep_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loade
     for (auto& kv : e->slots) n += kv.second.loaded ? 1 : 0;
     if (n_expected) *n_expected = (int)e->slots.size();
     if (n_loaded) *n_loaded = n;
+    return 0;
+}
+
+int l2h_sep_weight_info(void* handle, int32_t index, const char** name, int64_t* numel) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e) return fail(1, "null handle");
+    if (index < 0 || index >= (int32_t)e->slots.size()) return fail(1, "weight index out of range");
+    auto it = e->slots.begin();
+    std::advance(it, index);
+    if (name) *name = it->first.c_str();             // owned by the handle, valid until l2h_sep_destroy
+    if (numel) *numel = it->second.numel;
     return 0;
 }
 

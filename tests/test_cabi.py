@@ -118,3 +118,42 @@ def test_embed_weight_table_matches_reference_state_dict(lib, embed_params):
     assert lib.l2h_embed_max_batch(h, 80000, ctypes.byref(mb)) == 0 and mb.value >= 1
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 2, 8000))
+
+
+def test_weight_info_enumerates_the_state_dict(lib, tsh_params):
+    """l2h_sep_weight_info walks exactly the reference state_dict keys (minus buffers the engine ignores) with
+    their element counts -- what a non-Python host iterates over (examples/stream_clip.cpp)."""
+    from lookoncetohear_b200 import Net
+    net = Net(**tsh_params)
+    h = net._engine()
+    ne = ctypes.c_int32()
+    assert lib.l2h_sep_weights_expected(h, ctypes.byref(ne), None) == 0
+    sd = {k: v.numel() for k, v in net.state_dict().items()}
+    seen = {}
+    for i in range(ne.value):
+        name, numel = ctypes.c_char_p(), ctypes.c_int64()
+        assert lib.l2h_sep_weight_info(h, i, ctypes.byref(name), ctypes.byref(numel)) == 0
+        seen[name.value.decode()] = numel.value
+    assert seen == sd
+    assert lib.l2h_sep_weight_info(h, ne.value, None, None) != 0
+
+
+def test_cpp_host_example_builds(lib, tmp_path):
+    """examples/stream_clip.cpp (a host with no Python and no torch) compiles and links against the header and the
+    library; without a GPU it must stop at its first CUDA call with an error, not compute anything."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    cuda = "/usr/local/cuda"
+    if gxx is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("g++ / CUDA headers not available")
+    libdir = os.path.join(ROOT, "lookoncetohear_b200", "lib")
+    exe = str(tmp_path / "stream_clip")
+    cmd = [gxx, "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "stream_clip.cpp"), "-L", libdir, "-llookonce_b200",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and "l2h_sep_commit_weights" in r.stderr
