@@ -301,7 +301,7 @@ def main():
     extras = {}
     roof = None
     cpu_base = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras:          # extras are single-GPU figures (the N > 1 line carries value / e2e / roofline)
         # single-chunk latency: one call, synchronised, median of 200 (graph replay)
         st = net.init_buffers(1, dev)
         lat = []
