@@ -130,7 +130,8 @@ int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_p
 int l2h_sep_pipeline_frames(void* handle, int32_t* frames);
 /* runtime switches (also env L2H_PIPE / L2H_PDL / L2H_MID at create).  0 | 1: "pipeline" (wavefront graph for streams of
  * one-hop calls), "pdl", "fused_mid", "pipeline_split_mid" (mid section as mid_a | mid_b | mid_c in the graph),
- * "mid_split_large" (the same three kernels for many streams).  Counts: "pipeline_frames" (hops per graph, <= 500; 0 = as many as a 24 GB workspace holds),
+ * "mid_split_large" (the same three kernels for many streams), "fold_mid_c" (default 0, NOT YET RUN ON HARDWARE: no mid_c --
+ * the inter Linear moves into the serial kernel, the Q/K/V projection into qkv_kernel; changes rounding, not the maths).  Counts: "pipeline_frames" (hops per graph, <= 500; 0 = as many as a 24 GB workspace holds),
  * "pipeline_midb_hops" (hops per launch of the serial stage, <= 8) and the hops in flight per stage: "pipeline_lanes"
  * (BiLSTM, <= 12), "pipeline_midc_lanes" (<= 3), "pipeline_qkv_lanes" (<= 3), "pipeline_attn_lanes" (<= 4),
  * "pipeline_out_lanes" (<= 4), "pipeline_front_lanes" (<= 4), "pipeline_back_lanes" (<= 6).  Bit masks over the stages

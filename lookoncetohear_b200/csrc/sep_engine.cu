@@ -79,6 +79,7 @@ struct SepEngine {
     int pipe_flanes = 6;     // front_kernel hops in flight (<= PIPE_FLANES)
     int pipe_blanes = 6;     // back_kernel hops in flight (<= PIPE_BLANES)
     bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
+    bool fold_mid_c = false;      // no mid_c / no projection in the mid kernels: Linear in mid_b2, Q/K/V projection in qkv (untested)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
@@ -278,6 +279,8 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
+    CK(cudaFuncSetAttribute(mid_noproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
+    CK(cudaFuncSetAttribute(mid_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_B2_SMEM));
     CK(cudaFuncSetAttribute(mid_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_A_SMEM));
     CK(cudaFuncSetAttribute(mid_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_B_SMEM));
     CK(cudaFuncSetAttribute(mid_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_C_SMEM));
@@ -362,11 +365,18 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
             float* GI = GX; float* HN = GX + rows * 256;         // the BiLSTM is done with GX
             CK(launch_k(pdl, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st, (const float*)Y, X, GI, W, B));
-            CK(launch_k(pdl, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, st, (const float*)GI, HN, (int64_t)0, 1, state, ss, b, W, B));
-            CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B));
+            if (e->fold_mid_c) {
+                CK(launch_k(pdl, mid_b2_kernel, mid_grid_for(B, 2), dim3(256), MID_B2_SMEM, st, (const float*)GI, X, (int64_t)0, 1, state, ss, b, W, B));
+            } else {
+                CK(launch_k(pdl, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, st, (const float*)GI, HN, (int64_t)0, 1, state, ss, b, W, B));
+                CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B));
+            }
             MARK("mid");
         } else if (fused_mid) {
-            CK(launch_k(pdl, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
+            if (e->fold_mid_c)
+                CK(launch_k(pdl, mid_noproj_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
+            else
+                CK(launch_k(pdl, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
             MARK("mid");
         } else {
         g = GemmArgs{};
@@ -404,7 +414,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             MARK("kv_gather");
         }
         CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
-                    (const float*)(fused_mid ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
+                    (const float*)((fused_mid && !e->fold_mid_c) ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
         MARK("qkv");
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
@@ -482,6 +492,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
     // serial stage (mid_b -> mid_b of the next hop): everywhere, the parked dependents hold shared memory and CTA
     // slots the running kernels need (measured 14.0 vs 9.4 us per hop, profiles/r01f_pipeline_sweeps.jsonl)
     const int ppdl = e->pipe_pdl;         // stage bit mask (same bits as pipe_skip)
+    const bool fold = e->fold_mid_c;
     const bool many = mid_split_for_throughput(B);
     const bool split_mid = many ? e->mid_split_large : e->pipe_split_mid;
     float* state = a.state;
@@ -574,13 +585,21 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
             {
                 float* wsp = a.wsp + (int64_t)k0 * slot;
                 float* GI = wsp + ws.GX; float* HN = GI + (int64_t)rows * 256;
-                if (split_mid) {
+                if (split_mid && fold) {
+                    if (!(e->pipe_skip & 16))
+                        CK(launch_k((ppdl & 16) != 0, mid_b2_kernel, mid_grid_for(B, 2), dim3(256), MID_B2_SMEM, sB1(b), (const float*)GI, wsp + ws.X,
+                                    slot, k1 - k0, state, ss, b, W, B));
+                } else if (split_mid) {
                     if (!(e->pipe_skip & 16))
                         CK(launch_k((ppdl & 16) != 0, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, sB1(b), (const float*)GI, HN, slot,
                                     k1 - k0, state, ss, b, W, B));
                 } else if (!(e->pipe_skip & 16)) {
-                    CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y), wsp + ws.X,
-                                wsp + ws.QKVRAW, state, ss, b, W, B));
+                    if (fold)
+                        CK(launch_k((ppdl & 16) != 0, mid_noproj_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y),
+                                    wsp + ws.X, wsp + ws.QKVRAW, state, ss, b, W, B));
+                    else
+                        CK(launch_k((ppdl & 16) != 0, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, sB1(b), (const float*)(wsp + ws.Y),
+                                    wsp + ws.X, wsp + ws.QKVRAW, state, ss, b, W, B));
                 }
             }
             cudaEvent_t midb_done;
@@ -591,7 +610,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 float* X = wsp + ws.X; float* Z = wsp + ws.Z; float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW;
                 float* HN = wsp + ws.GX + (int64_t)rows * 256;
                 cudaStream_t st_q = sBq(b, k);
-                if (split_mid) {            // mid_c on its own lanes: the qkv lanes are held back by the ring guard
+                if (split_mid && !fold) {   // mid_c on its own lanes: the qkv lanes are held back by the ring guard
                     cudaStream_t st_c = sBc(b, k);
                     CK(cudaStreamWaitEvent(st_c, midb_done, 0));
                     if (!(e->pipe_skip & 32))
@@ -605,7 +624,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 for (int d = 0; d < e->pipe_tlanes && k - PIPE_QKV_AHEAD - 1 - d >= 0; ++d)
                     CK(cudaStreamWaitEvent(st_q, att_done[b][k - PIPE_QKV_AHEAD - 1 - d], 0));
                 if (!(e->pipe_skip & 64)) CK(launch_k((ppdl & 64) != 0, qkv_kernel, dim3(1, B), dim3(QKV_THREADS), QKV_SMEM, st_q, (const float*)X,
-                                                      (const float*)QKVRAW, Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
+                                                      (const float*)(fold ? nullptr : QKVRAW), Q, (float*)nullptr, (float*)nullptr, state, ss, b, W, 1, k));
                 if (int rc = record(&qkv_done[b][k], st_q)) return rc;
                 // the attention reads this hop's ring row and the 49 before it: the other qkv lanes' latest hops must be in
                 cudaStream_t st_t = sBa(b, k);
@@ -1056,6 +1075,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
+    else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else return fail(2, "unknown option: " + n);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting
     e->graphs.clear();
