@@ -367,10 +367,9 @@ inline cudaError_t launch_rows_gemm(const GemmArgs& g, cudaStream_t st, bool pdl
     if (g.ln_g && g.K != 64) return cudaErrorInvalidValue;
     if (g.M <= 2048) return launch_rows_gemm_cfg<16, 64, 2, 4>(g, st, pdl);     // 128 threads
     {   // large M: persistent kernel with the weight slab resident in shared memory (when it fits)
-        static const bool big = [] { const char* e = getenv("L2H_GEMM_BIG"); return e ? atoi(e) != 0 : true; }();
         const int bn = (g.N % 128 == 0) ? 128 : 64;
         const size_t smem = ((size_t)g.K * bn + (size_t)GK * 132) * sizeof(float);
-        if (big && smem <= 200 * 1024) return bn == 128 ? launch_rows_gemm_big<128>(g, st, pdl) : launch_rows_gemm_big<64>(g, st, pdl);
+        if (smem <= 200 * 1024) return bn == 128 ? launch_rows_gemm_big<128>(g, st, pdl) : launch_rows_gemm_big<64>(g, st, pdl);
     }
     if (g.N % 128 == 0) return launch_rows_gemm_cfg<64, 128, 4, 8>(g, st, pdl); // 256 threads
     return launch_rows_gemm_cfg<64, 64, 4, 4>(g, st, pdl);                      // 256 threads

@@ -3,9 +3,10 @@
 // The input projection W_ih x + b_ih + b_hh for all steps is a rows_gemm done beforehand
 // ("gx", gate columns packed as j*4 + q with q in {i,f,g,o}: thread tid of this kernel owns
 // column tid).  What is left is, per step, a 256x64 mat-vec with W_hh, the cell update and
-// one barrier -- a latency chain.  One CTA (256 threads) runs NSEQ independent sequences in
-// lock-step with W_hh row-resident in registers (64 regs/thread) and h broadcast through shared
-// memory; the FMAs are packed FFMA2 along k.
+// one barrier -- a latency chain.  One CTA (128 threads: hidden unit x k-half) runs NSEQ independent
+// sequences in lock-step with its W_hh slice in registers and h broadcast through shared memory; the
+// FMAs are packed FFMA2 along k.  lstm_rec3_kernel: few sequences (latency), lstm_rec4_kernel: many
+// sequences, the step written stage by stage across the CTA's sequences (throughput).
 //
 // Row addressing (rows of gx / out are activation rows of the [B,T,F,C] tensors):
 //   seq -> (o = seq / inner_count, i = seq % inner_count)
@@ -38,273 +39,6 @@ struct LstmArgs {
     int ndir;              // 1 or 2; direction 1 runs the steps in reverse
 };
 
-constexpr int LSTM_STAGES = 8;   // cp.async ring depth for the precomputed input projection
-
-template <int NSEQ>
-__global__ void __launch_bounds__(256, (NSEQ <= 4 ? 2 : 1))
-lstm_rec_kernel(const LstmArgs a) {
-    __shared__ __align__(16) float hbuf[2][NSEQ][64];
-    __shared__ __align__(16) float gs[LSTM_STAGES][NSEQ][256];   // gx rows, LSTM_STAGES steps in flight
-
-    griddep_launch();
-    const int tid = threadIdx.x;
-    const int dir = blockIdx.y;
-    const int seq0 = blockIdx.x * NSEQ;
-    const int j = tid >> 2, q = tid & 3;
-
-    // W_hh row (j*4+q) of this direction -> registers, as 32 k-pairs.  Independent of the chain:
-    // under PDL this overlaps the tail of the previous kernel.
-    float2 w[32];
-    {
-        const float4* wp = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + tid) * 64);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 t = __ldg(wp + k);
-            w[2 * k] = make_float2(t.x, t.y);
-            w[2 * k + 1] = make_float2(t.z, t.w);
-        }
-    }
-    griddep_wait();      // everything below reads what earlier kernels of the chain wrote
-
-    const bool own_out = (a.out_outer_stride | a.out_inner_stride | a.out_step_stride) != 0;
-    const int64_t o_step = (own_out ? a.out_step_stride : a.step_stride) * a.out_ld;   // floats per step
-    const int sgn = (dir == 0) ? 1 : -1;
-    const int first = (dir == 0) ? 0 : a.L - 1;
-
-    float c[NSEQ];
-    bool valid[NSEQ];
-    float* outp[NSEQ];          // &out[row(seq, first)][dir*64 + j]
-    int64_t hc[NSEQ];
-#pragma unroll
-    for (int s = 0; s < NSEQ; ++s) {
-        const int seq = seq0 + s;
-        valid[s] = seq < a.nseq;
-        const int sq = valid[s] ? seq : 0;
-        const int so = sq / a.inner_count, si = sq % a.inner_count;
-        const int64_t ob = own_out ? (int64_t)so * a.out_outer_stride + (int64_t)si * a.out_inner_stride
-                                   : (int64_t)so * a.outer_stride + (int64_t)si * a.inner_stride;
-        outp[s] = a.out + ob * a.out_ld + (int64_t)first * o_step + dir * 64 + j;
-        hc[s] = (int64_t)so * a.hc_outer_stride + (int64_t)si * 64 + j;
-        c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
-        if (q == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
-    }
-
-    // ---- gx ring: thread (cs = tid/64, chunk = tid%64) copies 16 B of sequence cs's row ----------
-    const int cs = tid >> 6, chunk = tid & 63;
-    const bool copier = cs < NSEQ && (seq0 + cs) < a.nseq;
-    const float* gsrc = nullptr;          // &gx[row(seq, first)][dir*256 + chunk*4]
-    const int64_t g_step = a.step_stride * a.gx_ld * sgn;
-    if (copier) {
-        const int sq = seq0 + cs;
-        const int64_t gb = (int64_t)(sq / a.inner_count) * a.outer_stride + (int64_t)(sq % a.inner_count) * a.inner_stride;
-        gsrc = a.gx + (gb + (int64_t)first * a.step_stride) * a.gx_ld + dir * 256 + chunk * 4;
-    }
-    auto issue = [&](int it) {           // copy the row of iteration `it` into its ring stage
-        if (copier && it < a.L) cp_async16(&gs[it % LSTM_STAGES][cs][chunk * 4], gsrc + (int64_t)it * g_step);
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int it = 0; it < LSTM_STAGES - 1; ++it) issue(it);
-    cp_async_wait<LSTM_STAGES - 2>();
-    __syncthreads();
-
-    // activation: sigmoid for i,f,o ; tanh for g (q == 2):  y = A / (1 + 2^(S x)) + Bc, S folds -log2(e)
-    const float S = (q == 2) ? -2.f * 1.4426950408889634f : -1.4426950408889634f;
-    const float Aa = (q == 2) ? 2.f : 1.f;
-    const float Bc = (q == 2) ? -1.f : 0.f;
-    const int qbase = (tid & 31) & ~3;
-
-    int cur = 0;
-    for (int it = 0; it < a.L; ++it) {
-        issue(it + LSTM_STAGES - 1);
-        const int stg = it % LSTM_STAGES;
-#pragma unroll
-        for (int s = 0; s < NSEQ; ++s) {
-            const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][s][0]);
-            float2 acc0 = make_float2(gs[stg][s][tid], 0.f), acc1 = make_float2(0.f, 0.f);
-            float2 acc2 = make_float2(0.f, 0.f), acc3 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-                const float4 h4 = hp[k], h5 = hp[k + 1];
-                acc0 = ffma2(w[2 * k], make_float2(h4.x, h4.y), acc0);
-                acc1 = ffma2(w[2 * k + 1], make_float2(h4.z, h4.w), acc1);
-                acc2 = ffma2(w[2 * k + 2], make_float2(h5.x, h5.y), acc2);
-                acc3 = ffma2(w[2 * k + 3], make_float2(h5.z, h5.w), acc3);
-            }
-            const float pre = ((acc0.x + acc0.y) + (acc1.x + acc1.y)) + ((acc2.x + acc2.y) + (acc3.x + acc3.y));
-            const float act = __fdividef(Aa, 1.f + ex2_ftz(S * pre)) + Bc;
-            const float gi = __shfl_sync(0xffffffffu, act, qbase + 0);
-            const float gf = __shfl_sync(0xffffffffu, act, qbase + 1);
-            const float gg = __shfl_sync(0xffffffffu, act, qbase + 2);
-            const float go = __shfl_sync(0xffffffffu, act, qbase + 3);
-            c[s] = gf * c[s] + gi * gg;
-            const float h = go * (__fdividef(2.f, 1.f + ex2_ftz(-2.f * 1.4426950408889634f * c[s])) - 1.f);
-            if (q == 0) {
-                hbuf[cur ^ 1][s][j] = h;
-                if (valid[s]) *outp[s] = h;
-            }
-            outp[s] += sgn * o_step;
-        }
-        cur ^= 1;
-        cp_async_wait<LSTM_STAGES - 2>();   // the row of iteration it+1 has landed (own copies) ...
-        __syncthreads();                    // ... and everybody's copies + the new h are visible
-    }
-
-    if (a.h_state != nullptr) {
-#pragma unroll
-        for (int s = 0; s < NSEQ; ++s) {
-            if (valid[s] && q == 0) {
-                a.h_state[hc[s]] = hbuf[cur][s][j];
-                a.c_state[hc[s]] = c[s];
-            }
-        }
-    }
-}
-
-// ---- variant 2: 128 threads, two gate rows per thread ---------------------------------------------
-// Thread (j = tid/2, half = tid%2) owns the rows of gates (i,f) [half 0] or (g,o) [half 1] of hidden
-// unit j: 128 weight registers, half the shared-memory broadcasts of h per FMA, a 4-warp barrier,
-// and only two shuffles per step.  Same arithmetic, same memory contract as lstm_rec_kernel.
-template <int NSEQ>
-__global__ void __launch_bounds__(128, 2)
-lstm_rec2_kernel(const LstmArgs a) {
-    __shared__ __align__(16) float hbuf[2][NSEQ][64];
-    __shared__ __align__(16) float gs[LSTM_STAGES][NSEQ][256];
-
-    griddep_launch();
-    const int tid = threadIdx.x;
-    const int dir = blockIdx.y;
-    const int seq0 = blockIdx.x * NSEQ;
-    const int j = tid >> 1, half = tid & 1;
-    const int col0 = j * 4 + half * 2;           // packed gate columns col0, col0 + 1
-
-    float2 w0[32], w1[32];
-    {
-        const float4* wp0 = reinterpret_cast<const float4*>(a.whh + ((int64_t)dir * 256 + col0) * 64);
-        const float4* wp1 = wp0 + 16;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 t0 = __ldg(wp0 + k), t1 = __ldg(wp1 + k);
-            w0[2 * k] = make_float2(t0.x, t0.y); w0[2 * k + 1] = make_float2(t0.z, t0.w);
-            w1[2 * k] = make_float2(t1.x, t1.y); w1[2 * k + 1] = make_float2(t1.z, t1.w);
-        }
-    }
-    griddep_wait();
-
-    const bool own_out = (a.out_outer_stride | a.out_inner_stride | a.out_step_stride) != 0;
-    const int64_t o_step = (own_out ? a.out_step_stride : a.step_stride) * a.out_ld;
-    const int sgn = (dir == 0) ? 1 : -1;
-    const int first = (dir == 0) ? 0 : a.L - 1;
-
-    float c[NSEQ];
-    bool valid[NSEQ];
-    float* outp[NSEQ];
-    int64_t hc[NSEQ];
-#pragma unroll
-    for (int s = 0; s < NSEQ; ++s) {
-        const int seq = seq0 + s;
-        valid[s] = seq < a.nseq;
-        const int sq = valid[s] ? seq : 0;
-        const int so = sq / a.inner_count, si = sq % a.inner_count;
-        const int64_t ob = own_out ? (int64_t)so * a.out_outer_stride + (int64_t)si * a.out_inner_stride
-                                   : (int64_t)so * a.outer_stride + (int64_t)si * a.inner_stride;
-        outp[s] = a.out + ob * a.out_ld + (int64_t)first * o_step + dir * 64 + j;
-        hc[s] = (int64_t)so * a.hc_outer_stride + (int64_t)si * 64 + j;
-        c[s] = (a.c_state != nullptr && valid[s]) ? a.c_state[hc[s]] : 0.f;
-        if (half == 0) hbuf[0][s][j] = (a.h_state != nullptr && valid[s]) ? a.h_state[hc[s]] : 0.f;
-    }
-
-    // gx ring: 64 x 16 B per (sequence, step); 128 threads cover two sequences per pass
-    const int64_t g_step = a.step_stride * a.gx_ld * sgn;
-    const float* gsrc[(NSEQ + 1) / 2];
-    bool copier[(NSEQ + 1) / 2];
-    const int chunk = tid & 63;
-#pragma unroll
-    for (int u = 0; u < (NSEQ + 1) / 2; ++u) {
-        const int cs = 2 * u + (tid >> 6);
-        copier[u] = cs < NSEQ && (seq0 + cs) < a.nseq;
-        gsrc[u] = nullptr;
-        if (copier[u]) {
-            const int sq = seq0 + cs;
-            const int64_t gb = (int64_t)(sq / a.inner_count) * a.outer_stride + (int64_t)(sq % a.inner_count) * a.inner_stride;
-            gsrc[u] = a.gx + (gb + (int64_t)first * a.step_stride) * a.gx_ld + dir * 256 + chunk * 4;
-        }
-    }
-    auto issue = [&](int it) {
-#pragma unroll
-        for (int u = 0; u < (NSEQ + 1) / 2; ++u)
-            if (copier[u] && it < a.L)
-                cp_async16(&gs[it % LSTM_STAGES][2 * u + (tid >> 6)][chunk * 4], gsrc[u] + (int64_t)it * g_step);
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int it = 0; it < LSTM_STAGES - 1; ++it) issue(it);
-    cp_async_wait<LSTM_STAGES - 2>();
-    __syncthreads();
-
-    const float LOG2E = 1.4426950408889634f;
-    // half 0: sigmoid(i), sigmoid(f);  half 1: tanh(g), sigmoid(o)
-    const float S0 = (half == 1) ? -2.f * LOG2E : -LOG2E, A0 = (half == 1) ? 2.f : 1.f, B0 = (half == 1) ? -1.f : 0.f;
-    const float S1 = -LOG2E;
-
-    int cur = 0;
-    for (int it = 0; it < a.L; ++it) {
-        issue(it + LSTM_STAGES - 1);
-        const int stg = it % LSTM_STAGES;
-#pragma unroll
-        for (int s = 0; s < NSEQ; ++s) {
-            const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][s][0]);
-            const float2 g2 = *reinterpret_cast<const float2*>(&gs[stg][s][col0]);
-            float2 a0 = make_float2(g2.x, 0.f), a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f), a3 = make_float2(0.f, 0.f);
-            float2 b0 = make_float2(g2.y, 0.f), b1 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f), b3 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-                const float4 h4 = hp[k], h5 = hp[k + 1];
-                const float2 hA = make_float2(h4.x, h4.y), hB = make_float2(h4.z, h4.w);
-                const float2 hC = make_float2(h5.x, h5.y), hD = make_float2(h5.z, h5.w);
-                a0 = ffma2(w0[2 * k], hA, a0); b0 = ffma2(w1[2 * k], hA, b0);
-                a1 = ffma2(w0[2 * k + 1], hB, a1); b1 = ffma2(w1[2 * k + 1], hB, b1);
-                a2 = ffma2(w0[2 * k + 2], hC, a2); b2 = ffma2(w1[2 * k + 2], hC, b2);
-                a3 = ffma2(w0[2 * k + 3], hD, a3); b3 = ffma2(w1[2 * k + 3], hD, b3);
-            }
-            const float p0 = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
-            const float p1 = ((b0.x + b0.y) + (b1.x + b1.y)) + ((b2.x + b2.y) + (b3.x + b3.y));
-            const float e0 = ex2_ftz(S0 * p0), e1 = ex2_ftz(S1 * p1);
-            const float v0 = __fdividef(A0, 1.f + e0) + B0;      // half0: i      half1: g
-            const float v1 = __fdividef(1.f, 1.f + e1);          // half0: f      half1: o
-            const float og = __shfl_xor_sync(0xffffffffu, v0, 1);  // half0 receives g
-            const float oo = __shfl_xor_sync(0xffffffffu, v1, 1);  // half0 receives o
-            // (half 1 computes the same expressions on swapped operands; its results are unused)
-            c[s] = v1 * c[s] + v0 * og;
-            const float h = oo * (__fdividef(2.f, 1.f + ex2_ftz(-2.f * LOG2E * c[s])) - 1.f);
-            if (half == 0) {
-                hbuf[cur ^ 1][s][j] = h;
-                if (valid[s]) *outp[s] = h;
-            }
-            outp[s] += sgn * o_step;
-        }
-        cur ^= 1;
-        cp_async_wait<LSTM_STAGES - 2>();
-        __syncthreads();
-    }
-    if (a.h_state != nullptr) {
-#pragma unroll
-        for (int s = 0; s < NSEQ; ++s) {
-            if (valid[s] && half == 0) {
-                a.h_state[hc[s]] = hbuf[cur][s][j];
-                a.c_state[hc[s]] = c[s];
-            }
-        }
-    }
-}
-
-// ---- variant 3 (default): 128 threads, thread = (hidden unit j, k-half) --------------------------
-// Measured on B200 (profiles/r01c_lstm_microbench.txt): a broadcast LDS.128 still costs 4 LSU passes, so
-// the 16 x 8-warp broadcasts of h per step of variant 1 are the step's largest cost (340 ns/step; 230 ns
-// with every MUFU, copy and store removed).  Here a thread owns all FOUR gate rows of unit j over HALF
-// of k: 8 LDS.128 feed 64 FFMA2 (4x the FMAs per shared-memory byte of variant 1), the two k-halves
-// meet with one shuffle-add per gate, and both lanes then hold all four pre-activations, so the gate
-// exchange needs only two more shuffles.
 // PRE = true: the whole input projection of the sequence (L x 1 KB) is brought in up front by TMA bulk
 // copies (one per step row) -- no per-step async bookkeeping at all; used when it fits (short L).
 // PRE = false: 8-stage cp.async ring refilled four rows (one group) at a time.
@@ -631,12 +365,6 @@ lstm_rec4_kernel(const LstmArgs a) {
     }
 }
 
-inline int lstm_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("L2H_LSTM_V"); v = e ? atoi(e) : 3; }
-    return v;
-}
-
 inline cudaError_t configure_lstm() {
     cudaError_t e = cudaFuncSetAttribute(lstm_rec3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
@@ -644,45 +372,15 @@ inline cudaError_t configure_lstm() {
 
 inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st, bool pdl = false) {
     if (a.nseq <= 0 || a.L <= 0) return cudaErrorInvalidValue;
-    if (lstm_variant() == 3) {
-        const int ctas1 = a.nseq * a.ndir;
-        if (ctas1 <= 148 && (size_t)a.L * 1024 <= 200 * 1024) {      // latency mode: one sequence per CTA, preloaded
-            return launch_k(pdl, lstm_rec3_kernel<1, true>, dim3(a.nseq, a.ndir), dim3(128), (size_t)a.L * 1024, st, a);
-        }
-        int per = 1;
-        while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
-        static const int force_per = [] { const char* e = getenv("L2H_LSTM_PER"); return e ? atoi(e) : 0; }();
-        static const bool staged = [] { const char* e = getenv("L2H_LSTM_STAGED"); return e ? atoi(e) != 0 : true; }();
-        if (force_per == 1 || force_per == 2 || force_per == 4) per = force_per;
-        dim3 grid((a.nseq + per - 1) / per, a.ndir);
-        if (staged && per == 2) return launch_k(pdl, lstm_rec4_kernel<2>, grid, dim3(128), 0, st, a);
-        if (staged && per == 4) return launch_k(pdl, lstm_rec4_kernel<4>, grid, dim3(128), 0, st, a);
-        switch (per) {
-            case 1: return launch_k(pdl, lstm_rec3_kernel<1, false>, grid, dim3(128), 0, st, a);
-            case 2: return launch_k(pdl, lstm_rec3_kernel<2, false>, grid, dim3(128), 0, st, a);
-            default: return launch_k(pdl, lstm_rec3_kernel<4, false>, grid, dim3(128), 0, st, a);
-        }
-    }
-    if (lstm_variant() == 2) {
-        int per = 1;
-        while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
-        dim3 grid((a.nseq + per - 1) / per, a.ndir);
-        switch (per) {
-            case 1: return launch_k(pdl, lstm_rec2_kernel<1>, grid, dim3(128), 0, st, a);
-            case 2: return launch_k(pdl, lstm_rec2_kernel<2>, grid, dim3(128), 0, st, a);
-            default: return launch_k(pdl, lstm_rec2_kernel<4>, grid, dim3(128), 0, st, a);
-        }
-    }
-    // smallest NSEQ that still fits one wave of 148 SMs x 2 CTAs
-    const int slots = 296;
-    int nseq_per = 1;
-    while (nseq_per < 4 && ((a.nseq + nseq_per - 1) / nseq_per) * a.ndir > slots) nseq_per *= 2;
-    dim3 grid((a.nseq + nseq_per - 1) / nseq_per, a.ndir);
-    switch (nseq_per) {
-        case 1: return launch_k(pdl, lstm_rec_kernel<1>, grid, dim3(256), 0, st, a);
-        case 2: return launch_k(pdl, lstm_rec_kernel<2>, grid, dim3(256), 0, st, a);
-        default: return launch_k(pdl, lstm_rec_kernel<4>, grid, dim3(256), 0, st, a);
-    }
+    const int ctas1 = a.nseq * a.ndir;
+    if (ctas1 <= 148 && (size_t)a.L * 1024 <= 200 * 1024)      // latency mode: one sequence per CTA, preloaded
+        return launch_k(pdl, lstm_rec3_kernel<1, true>, dim3(a.nseq, a.ndir), dim3(128), (size_t)a.L * 1024, st, a);
+    int per = 1;
+    while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
+    dim3 grid((a.nseq + per - 1) / per, a.ndir);
+    if (per == 2) return launch_k(pdl, lstm_rec4_kernel<2>, grid, dim3(128), 0, st, a);   // many sequences: stage by stage
+    if (per == 4) return launch_k(pdl, lstm_rec4_kernel<4>, grid, dim3(128), 0, st, a);
+    return launch_k(pdl, lstm_rec3_kernel<1, false>, grid, dim3(128), 0, st, a);
 }
 
 }  // namespace l2h

@@ -49,6 +49,9 @@ struct SepEngine {
     int n_blocks;
     std::vector<float> host;        // staging
     float* dev = nullptr;           // packed weights
+    int device = -1;                // ordinal of the device that owns `dev`, the streams, events and cached graphs
+    int64_t weight_gen = 0;         // bumped by every commit
+    bool graph_stats = false;
     int64_t total = 0;
     std::map<std::string, Slot> slots;
     SepWeights w;
@@ -78,11 +81,11 @@ struct SepEngine {
     int pipe_olanes = 4;     // attn_out hops in flight per block (<= PIPE_OLANES)
     int pipe_flanes = 6;     // front_kernel hops in flight (<= PIPE_FLANES)
     int pipe_blanes = 6;     // back_kernel hops in flight (<= PIPE_BLANES)
-    bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (L2H_PIPE=0 disables)
+    bool use_pipe = true;    // wavefront pipelining of one-frame calls inside a multi-frame graph (option "pipeline")
     bool fold_mid_c = false;      // no mid_c / no projection in the mid kernels: Linear in mid_b2, Q/K/V projection in qkv (untested)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
-    bool use_mid = true;     // fused row-local mid-section for one-frame calls (L2H_MID=0 disables)
-    bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (L2H_PDL=0 disables)
+    bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
+    bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
 };
 
 static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
@@ -221,8 +224,13 @@ static void build_layout(SepEngine* e) {
     for (auto& f : fix) *f.first = reinterpret_cast<const float*>(f.second);
 }
 
-static void resolve_pointers(SepEngine* e) {
-    auto fixp = [&](const float*& p) { p = e->dev + reinterpret_cast<int64_t>(p); };
+// pointer fields hold offsets (floats) until the first commit; `base` turns them into device addresses, and a
+// later re-commit on another device shifts them by (new base - old base)
+static void shift_pointers(SepEngine* e, const float* new_base, const float* old_base) {
+    auto fixp = [&](const float*& p) {
+        if (old_base == nullptr) p = new_base + reinterpret_cast<int64_t>(p);      // offset -> address
+        else p = new_base + (p - old_base);                                        // address on the old device -> new one
+    };
     SepWeights& w = e->w;
     fixp(w.wat); fixp(w.ws); fixp(w.wc); fixp(w.bc); fixp(w.we); fixp(w.be); fixp(w.lne_g); fixp(w.lne_b);
     fixp(w.wd); fixp(w.bd);
@@ -271,9 +279,13 @@ static inline dim3 mid_grid_for(int B, int ctas_per_sm) { return dim3(std::min(1
 // three smaller kernels run 2-4 CTAs per SM (same arithmetic, +3 small global round trips)
 static inline bool mid_split_for_throughput(int B) { return mid_items(B) > 148; }
 
-static bool g_attr_done = false;
+// cudaFuncSetAttribute applies to the CURRENT device: keep one flag per device ordinal
+static bool g_attr_done[64] = {};
 static int set_attrs() {
-    if (g_attr_done) return 0;
+    int dev_ord = 0;
+    CK(cudaGetDevice(&dev_ord));
+    if (dev_ord < 0 || dev_ord >= 64) return fail(1, "device ordinal out of range");
+    if (g_attr_done[dev_ord]) return 0;
     CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
@@ -286,7 +298,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(mid_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_C_SMEM));
     CK(configure_rows_gemm());
     CK(configure_lstm());
-    g_attr_done = true;
+    g_attr_done[dev_ord] = true;
     return 0;
 }
 
@@ -695,7 +707,7 @@ static int run_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t st
         const cudaError_t ce = cudaStreamEndCapture(origin, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return fail(3, std::string("cudaStreamEndCapture (pipeline): ") + cudaGetErrorString(ce));
-        if (getenv("L2H_GRAPH_STATS")) {            // debug: node / edge census of the captured pipeline graph
+        if (e->graph_stats) {                       // debug (option "graph_stats"): node / edge census of the captured pipeline graph
             size_t n_nodes = 0, n_edges = 0;
             cudaGraphGetNodes(graph, nullptr, &n_nodes);
             cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &n_edges);
@@ -776,22 +788,42 @@ int l2h_sep_create(const l2h_sep_config* c, void** handle) {
     SepEngine* e = new SepEngine();
     e->cfg = *c;
     e->n_blocks = c->B;
-    if (const char* v = getenv("L2H_PDL")) e->use_pdl = atoi(v) != 0;
-    if (const char* v = getenv("L2H_MID")) e->use_mid = atoi(v) != 0;
-    if (const char* v = getenv("L2H_PIPE")) e->use_pipe = atoi(v) != 0;
     build_layout(e);
     *handle = e;
+    return 0;
+}
+
+// everything the handle owns on its device: cached graphs, capture / pipeline streams, events, the weight buffer
+static void release_device_resources(SepEngine* e) {
+    int cur = -1;
+    const bool sw = e->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != e->device;
+    if (sw) cudaSetDevice(e->device);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+    e->graph_kernels.clear();
+    if (e->cap_stream) { cudaStreamDestroy(e->cap_stream); e->cap_stream = nullptr; }
+    for (auto& ps : e->pipe_streams) if (ps) { cudaStreamDestroy(ps); ps = nullptr; }
+    for (auto& ev : e->pipe_events) cudaEventDestroy(ev);
+    e->pipe_events.clear();
+    if (e->trace_dev) { cudaFree(e->trace_dev); e->trace_dev = nullptr; e->trace_cap = 0; }
+    if (e->dev) { cudaFree(e->dev); e->dev = nullptr; }
+    if (sw) cudaSetDevice(cur);
+}
+
+// a handle is bound to the device that was current at its last commit (one handle per device)
+static int check_device(SepEngine* e) {
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (e->device >= 0 && cur != e->device)
+        return fail(1, "this handle's weights live on device " + std::to_string(e->device) + " but device " + std::to_string(cur) +
+                       " is current: commit the weights again with the new device current (Net.to(device) does), or use one handle per device");
     return 0;
 }
 
 int l2h_sep_destroy(void* handle) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e) return 0;
-    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
-    for (auto& ps : e->pipe_streams) if (ps) cudaStreamDestroy(ps);
-    for (auto& ev : e->pipe_events) cudaEventDestroy(ev);
-    if (e->dev) cudaFree(e->dev);
+    release_device_resources(e);
     delete e;
     return 0;
 }
@@ -856,12 +888,31 @@ int l2h_sep_commit_weights(void* handle, void* stream) {
             for (int n = 0; n < M6_N; ++n) h[m.dst + MID_W6 + mid_widx(M6_KS, M6_N, k, n)] = h[m.wqkv + (int64_t)k * NQKV + n];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool first = (e->dev == nullptr);
-    if (first) CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    const float* old_base = e->dev;              // null before the first commit (pointer fields then hold offsets)
+    if (e->dev != nullptr && e->device != cur) {  // the module moved to another GPU: everything device-side is rebuilt there
+        release_device_resources(e);
+    }
+    if (e->dev == nullptr) {
+        CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
+        e->device = cur;
+        shift_pointers(e, e->dev, old_base);
+    }
     CK(cudaMemcpyAsync(e->dev, e->host.data(), e->total * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    if (first) resolve_pointers(e);
     e->committed = true;
+    ++e->weight_gen;
+    return 0;
+}
+
+int l2h_sep_state_offsets(void* handle, int64_t* out, int32_t n) {
+    SepEngine* e = static_cast<SepEngine*>(handle);
+    if (!e || !out) return fail(1, "null argument");
+    const int64_t v[L2H_STATE_OFFSETS] = {RING, QK_LD, QK_DIM, V_DIM, ATT, ST_EMB, ST_GATE, ST_CONV, ST_DECONV, ST_ISTFT, ST_BLK,
+                                          BK_K, BK_V, BK_H, BK_C, BK_STRIDE};
+    if (n < L2H_STATE_OFFSETS) return fail(1, "need room for L2H_STATE_OFFSETS values");
+    for (int i = 0; i < L2H_STATE_OFFSETS; ++i) out[i] = v[i];
     return 0;
 }
 
@@ -963,6 +1014,7 @@ int l2h_sep_forward(void* handle, const float* x, int64_t xbs, int64_t xcs, int3
                     void* state, float* y, int64_t ybs, int64_t ycs, int32_t y_len, int32_t batch, int32_t frames,
                     void* ws, size_t ws_bytes, uint32_t flags, void* stream) {
     SepEngine* e = static_cast<SepEngine*>(handle);
+    if (e) { if (int rc_dev = check_device(e)) return rc_dev; }
     if (!e || !x || !emb || !state || !y || !ws) return fail(1, "null argument");
     ChainArgs a{x, xbs, xcs, x_len, emb, static_cast<float*>(state), y, ybs, ycs, y_len, batch, frames,
                 static_cast<float*>(ws), ws_bytes, flags & ~L2H_FLAG_GRAPH, 0};
@@ -973,6 +1025,7 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
                         float* y_host, int32_t y_len, int32_t batch, int32_t n_calls, int32_t cpc,
                         float* x_stage, float* y_stage, void* ws, size_t ws_bytes, void* stream) {
     SepEngine* e = static_cast<SepEngine*>(handle);
+    if (e) { if (int rc_dev = check_device(e)) return rc_dev; }
     if (!e || !x_host || !emb || !state || !y_host || !x_stage || !y_stage || !ws) return fail(1, "null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // hops moved per host<->device round: one call's worth, or (one-hop calls, pipelining on) a group of up to
@@ -1011,6 +1064,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
                        float* y_dev, int32_t y_len, int32_t batch, int32_t n_calls, int32_t cpc, void* ws,
                        size_t ws_bytes, void* stream) {
     SepEngine* e = static_cast<SepEngine*>(handle);
+    if (e) { if (int rc_dev = check_device(e)) return rc_dev; }
     if (!e || !x_dev || !emb || !state || !y_dev || !ws) return fail(1, "null argument");
     if (n_calls <= 0 || cpc <= 0) return fail(1, "n_calls and chunks_per_call must be positive");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1094,6 +1148,7 @@ int l2h_sep_profile(void* handle, const float* x_dev, int32_t x_len, const float
                     int32_t batch, int32_t frames, void* ws, size_t ws_bytes, int32_t iters, const char** names,
                     float* ms_total, int32_t* counts, int32_t* n_names, void* stream) {
     SepEngine* e = static_cast<SepEngine*>(handle);
+    if (e) { if (int rc_dev = check_device(e)) return rc_dev; }
     if (!e || !x_dev || !emb || !state || !y_dev || !ws || !names || !ms_total || !counts || !n_names)
         return fail(1, "null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

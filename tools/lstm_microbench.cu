@@ -11,7 +11,7 @@ template <bool RING, bool STG, bool TANHC, bool ACT, bool BAR8>
 __global__ void __launch_bounds__(256, 2)
 exp_kernel(const float* __restrict__ gx, float* __restrict__ out, const float* __restrict__ whh, int L) {
     __shared__ __align__(16) float hbuf[2][64];
-    __shared__ __align__(16) float gs[LSTM_STAGES][256];
+    __shared__ __align__(16) float gs[8][256];
     const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;
     float2 w[32];
     const float4* wp = reinterpret_cast<const float4*>(whh + (int64_t)tid * 64);
@@ -20,9 +20,9 @@ exp_kernel(const float* __restrict__ gx, float* __restrict__ out, const float* _
     if (q == 0) hbuf[0][j] = 0.f;
     float c = 0.f;
     auto issue = [&](int it) {
-        if (RING) { if (tid < 64 && it < L) cp_async16(&gs[it % LSTM_STAGES][tid * 4], gx + (int64_t)it * 256 + tid * 4); cp_async_commit(); }
+        if (RING) { if (tid < 64 && it < L) cp_async16(&gs[it % 8][tid * 4], gx + (int64_t)it * 256 + tid * 4); cp_async_commit(); }
     };
-    if (RING) { for (int it = 0; it < LSTM_STAGES - 1; ++it) issue(it); cp_async_wait<LSTM_STAGES - 2>(); }
+    if (RING) { for (int it = 0; it < 8 - 1; ++it) issue(it); cp_async_wait<8 - 2>(); }
     __syncthreads();
     const float S = (q == 2) ? -2.f * 1.4426950408889634f : -1.4426950408889634f;
     const float Aa = (q == 2) ? 2.f : 1.f, Bc = (q == 2) ? -1.f : 0.f;
@@ -30,8 +30,8 @@ exp_kernel(const float* __restrict__ gx, float* __restrict__ out, const float* _
     int cur = 0;
     float* op = out + j;
     for (int it = 0; it < L; ++it) {
-        issue(it + LSTM_STAGES - 1);
-        const float g0 = RING ? gs[it % LSTM_STAGES][tid] : 0.01f * (float)(tid & 7);
+        issue(it + 8 - 1);
+        const float g0 = RING ? gs[it % 8][tid] : 0.01f * (float)(tid & 7);
         const float4* hp = reinterpret_cast<const float4*>(&hbuf[cur][0]);
         float2 a0 = make_float2(g0, 0.f), a1 = make_float2(0.f, 0.f), a2 = a1, a3 = a1;
 #pragma unroll
@@ -49,7 +49,7 @@ exp_kernel(const float* __restrict__ gx, float* __restrict__ out, const float* _
         if (q == 0) { hbuf[cur ^ 1][j] = h; if (STG) *op = h; }
         op += 128;
         cur ^= 1;
-        if (RING) cp_async_wait<LSTM_STAGES - 2>();
+        if (RING) cp_async_wait<8 - 2>();
         if (BAR8) __syncthreads();
         else asm volatile("bar.sync 1, 256;");
     }
@@ -80,8 +80,6 @@ int main() {
     a.gx = gx; a.gx_ld = 512; a.out = out; a.out_ld = 128; a.whh = whh; a.nseq = 1; a.L = L; a.inner_count = 1;
     a.outer_stride = L; a.inner_stride = 0; a.step_stride = 1; a.ndir = 2;
     auto rep = [&](const char* name, float ms) { printf("%-46s %8.1f ns/step\n", name, 1e6f * ms / L); };
-    rep("v1 lstm_rec_kernel<1> (256 thr, 2 dirs on 2 SMs)", time_it([&] { lstm_rec_kernel<1><<<dim3(1, 2), 256>>>(a); }));
-    rep("v2 lstm_rec2_kernel<1> (128 thr x 2 rows)", time_it([&] { lstm_rec2_kernel<1><<<dim3(1, 2), 128>>>(a); }));
     rep("v3 lstm_rec3_kernel<1,ring> (128 thr, unit x k-half)", time_it([&] { lstm_rec3_kernel<1, false><<<dim3(1, 2), 128>>>(a); }));
     {
         cudaFuncSetAttribute(lstm_rec3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -91,14 +89,9 @@ int main() {
         b.L = 97; b.outer_stride = 97;
         ms = time_it([&] { lstm_rec3_kernel<1, true><<<dim3(1, 2), 128, 97 * 1024>>>(b); });
         printf("%-46s %8.2f us per launch (L=97, both directions)\n", "v3 preload, the T=1 intra launch", 1e3f * ms);
-        LstmArgs c1 = a; c1.L = 97; c1.outer_stride = 97;
-        ms = time_it([&] { lstm_rec_kernel<1><<<dim3(1, 2), 256>>>(c1); });
-        printf("%-46s %8.2f us per launch (L=97, both directions)\n", "v1, the T=1 intra launch", 1e3f * ms);
     }
     a.nseq = 4;  a.outer_stride = L / 4; a.L = L / 4;
     { float ms = time_it([&] { lstm_rec3_kernel<4, false><<<dim3(1, 2), 128>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v3 NSEQ=4", 1e6f * ms / (L / 4)); }
-    { float ms = time_it([&] { lstm_rec_kernel<4><<<dim3(1, 2), 256>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v1 NSEQ=4", 1e6f * ms / (L / 4)); }
-    { float ms = time_it([&] { lstm_rec2_kernel<4><<<dim3(1, 2), 128>>>(a); }); printf("%-46s %8.1f ns/step (4 seqs in lock-step)\n", "v2 NSEQ=4", 1e6f * ms / (L / 4)); }
     rep("exp: full (ring, stg, tanh, act, bar0)", time_it([&] { exp_kernel<true, true, true, true, true><<<1, 256>>>(gx, out, whh, L); }));
     rep("exp: no ring (gx const)", time_it([&] { exp_kernel<false, true, true, true, true><<<1, 256>>>(gx, out, whh, L); }));
     rep("exp: no per-step STG", time_it([&] { exp_kernel<true, false, true, true, true><<<1, 256>>>(gx, out, whh, L); }));
