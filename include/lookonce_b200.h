@@ -84,6 +84,13 @@ int l2h_sep_state_bytes(void* handle, int32_t batch, size_t* bytes);
 int l2h_sep_state_init(void* handle, void* state_dev, int32_t batch, void* stream);
 /* floats per stream record and header bytes, for host code that builds views of the state */
 int l2h_sep_state_layout(void* handle, int64_t* header_bytes, int64_t* stream_stride_floats);
+/* The offsets (in floats) inside one stream record, for host code that converts to / from the reference's nested
+ * state dict (tfgridnet_causal.py:173-186, :408-427) -- SepState.to_reference() / load_reference().  out[i]:
+ * 0 ring slots per head, 1 K row stride, 2 K row length (582), 3 V row length (1552), 4 attention window (50),
+ * 5 embedding copy, 6 cached speaker gate, 7 conv tail, 8 deconv tail, 9 iSTFT tail, 10 first block, then inside a
+ * block: 11 K ring, 12 V ring, 13 h, 14 c, 15 block stride. */
+#define L2H_STATE_OFFSETS 16
+int l2h_sep_state_offsets(void* handle, int64_t* out, int32_t n);
 
 int l2h_sep_workspace_bytes(void* handle, int32_t batch, int32_t frames, uint32_t flags, size_t* bytes);
 
@@ -189,11 +196,26 @@ int l2h_embed_load_weight(void* handle, const char* name, const float* host_data
 int l2h_embed_weights_expected(void* handle, int32_t* n_expected, int32_t* n_loaded);
 int l2h_embed_commit_weights(void* handle, void* stream);
 int l2h_embed_workspace_bytes(void* handle, int32_t batch, int32_t n_samples, size_t* bytes);
+/* "bf16" = 1: the tensor-core GEMMs take plain bf16 operands (one MMA pass); 0 (default): every product is formed from
+ * bf16 hi/lo splits of both fp32 operands in three MMA passes (fp32-grade, relative error ~2^-16 per product). */
+int l2h_embed_set_option(void* handle, const char* name, int32_t value);
 /* largest batch one l2h_embed_forward call should be given for utterances of n_samples (workspace bound) */
 int l2h_embed_max_batch(void* handle, int32_t n_samples, int32_t* max_batch);
 /* x_dev [batch][2][n_samples] fp32 contiguous -> emb_dev [batch][256].  Asynchronous on `stream`. */
 int l2h_embed_forward(void* handle, const float* x_dev, float* emb_dev, int32_t batch, int32_t n_samples,
                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation epilogue on the device (replaces the CPU metric code after `outputs.cpu()` in
+ * src/ts_hear_test.py:139-146): per mixture b, out_dev[b] = { output_sisnr, si_snr_i, embedding_sim }
+ *   output_sisnr  = mean over channels of SI-SNR(est, target)                 (torchmetrics definition, zero-mean)
+ *   si_snr_i      = mean over channels of SI-SNR(est, target) - SI-SNR(mixture, target)   (0 if mixture_dev is NULL)
+ *   embedding_sim = cosine similarity of emb and emb_gt                        (0 if either is NULL)
+ * est / target / mixture: [batch][channels][n_samples] fp32 contiguous on the device (est = the separator's output
+ * buffer); emb / emb_gt: [batch][emb_dim].  Asynchronous on `stream`; the caller copies 3 floats per mixture back. */
+int l2h_eval_metrics(const float* est_dev, const float* target_dev, const float* mixture_dev, int32_t batch, int32_t channels,
+                     int32_t n_samples, const float* emb_dev, const float* emb_gt_dev, int32_t emb_dim, float* out_dev,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,10 @@ struct TraceScope {
     }
 };
 
+// every kernel launch the engines issue goes through launch_k / launch_cluster / umma::launch: this counter makes the
+// "kernels launched" figure of the C ABI exact for directly launched chains (graph replays count their kernel nodes)
+inline thread_local long long g_launches = 0;
+
 // host: launch with (or without) the PDL attribute
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -160,6 +164,7 @@ inline cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    ++g_launches;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -176,6 +181,7 @@ inline cudaError_t launch_cluster(bool pdl, dim3 cluster, void (*kernel)(KArgs..
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
+    ++g_launches;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 }  // namespace l2h

@@ -13,8 +13,8 @@
 
 #include "../../include/lookonce_b200.h"
 #include "embed_kernels.cuh"
-#include "gemm.cuh"
 #include "lstm.cuh"
+#include "umma_host.cuh"
 
 namespace l2h {
 
@@ -49,8 +49,29 @@ struct EmbedEngine {
     EmbWeights w;
     std::vector<EmbBlockWeights> bw;
     bool committed = false;
-    bool attrs = false;
+    int attrs_dev = -1;
+    int device = -1;
+    // bf16 hi/lo planes [2][N][K] of every tensor-core B operand, built on the device at commit from the packed fp32
+    // k-major matrices (csrc/umma_host.cuh: split_planes)
+    struct PlaneSrc { int64_t wt_off; int K, N; int64_t plane_off; };
+    std::vector<PlaneSrc> plane_srcs;
+    __nv_bfloat16* planes = nullptr;
+    int64_t planes_total = 0;
+    int passes = 3;                 // 3: bf16x3 split products (fp32-grade), 1: plain bf16 operands
 };
+
+static umma::BPlanes wplanes(const EmbedEngine* e, const float* wt, int K, int N) {
+    // the packed matrices were registered in order; look the plane set up by device address
+    const int64_t off = wt - e->dev;
+    for (const auto& ps : e->plane_srcs)
+        if (ps.wt_off == off) {
+            umma::BPlanes b;
+            b.base = e->planes + ps.plane_off; b.ld = K; b.z_stride = 0; b.plane_stride = e->planes_total; b.nz = 1; b.mn_major = false;
+            (void)N;
+            return b;
+        }
+    return umma::BPlanes{};
+}
 
 static inline int perm_row(int p) { return (p & 3) * 64 + (p >> 2); }
 
@@ -205,6 +226,19 @@ static void build_layout(EmbedEngine* e) {
     }
     e->total = cur;
     e->host.assign(cur, 0.f);
+    {   // tensor-core B operands (offsets are still offsets here)
+        int64_t pc = 0;
+        auto reg = [&](const float* field, int K, int N) {
+            e->plane_srcs.push_back({reinterpret_cast<int64_t>(field), K, N, pc});
+            pc += ((int64_t)K * N + 63) & ~int64_t(63);
+        };
+        for (auto& f : fix) *f.first = reinterpret_cast<const float*>(f.second);      // stash offsets first
+        reg(e->w.wh_t, FC, 256);
+        for (auto& W : e->bw) {
+            reg(W.wih1_t, 256, 512); reg(W.wl1_t, 512, 64); reg(W.wih2_t, 256, 512); reg(W.wl2_t, 512, 64); reg(W.wqkv_t, 64, NQKV);
+        }
+        e->planes_total = pc;
+    }
     for (int n = 0; n < NFFT; ++n) {
         const double win = 0.5 - 0.5 * std::cos(2.0 * M_PI * n / NFFT);
         for (int k = 0; k < NF; ++k) {
@@ -228,7 +262,7 @@ static void resolve(EmbedEngine* e) {
     }
 }
 
-struct EWs { int64_t INV, GN, X, A, GX, HC, QKV, QN, KN, VN, S, O, HD, total; int T, Tp; };
+struct EWs { int64_t INV, GN, X, GX, HC, QKV, QN, KP, VP, S, O, HD, total; int T, Tp; };
 
 static EWs ecarve(int B, int N) {
     EWs w;
@@ -240,21 +274,27 @@ static EWs ecarve(int B, int N) {
     w.INV = alloc(B);
     w.GN = alloc(4 * B);                       // 2 doubles per utterance
     w.X = alloc(rows * 64);
-    w.A = alloc(rows * 64);
-    const int64_t gx_rows = std::max((int64_t)B * T * (NF - KS + 1), (int64_t)B * NF * (T - KS + 1));
-    w.GX = alloc(gx_rows * 512);
-    const int64_t hc_rows = std::max((int64_t)B * T * (NF - KS + 1 + 6), (int64_t)B * NF * (T - KS + 1 + 6));
-    w.HC = alloc(hc_rows * 128);
+    const int64_t seq_rows = std::max((int64_t)B * T * (NF - KS + 1), (int64_t)B * NF * (T - KS + 1));
+    w.GX = alloc(seq_rows * 512);
+    w.HC = alloc(seq_rows * 128);
     w.QKV = alloc(rows * NQKV);
     w.QN = alloc((int64_t)B * NH * Tp * QK);
-    w.KN = alloc((int64_t)B * NH * Tp * QK);
-    w.VN = alloc((int64_t)B * NH * Tp * VDIM);
+    w.KP = alloc((int64_t)B * NH * Tp * QK);    // two bf16 planes = one float per element
+    w.VP = alloc((int64_t)B * NH * Tp * VDIM);
     w.S = alloc((int64_t)B * NH * T * Tp);
     w.O = alloc((int64_t)B * NH * Tp * VDIM);
     w.HD = alloc((int64_t)B * T * 256);
     w.total = cur;
     return w;
 }
+
+#define CKU(expr)                                                                                  \
+    do {                                                                                           \
+        std::string _why;                                                                          \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(3, std::string(#expr) + ": " + cudaGetErrorString(_e) + " " + _why);       \
+    } while (0)
 
 static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B, int N, float* wsp, size_t ws_bytes,
                               cudaStream_t st) {
@@ -266,16 +306,26 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
     if (T < KS) return fail(1, "utterance too short for the 4-frame unfold");
     const int64_t rows = (int64_t)B * T * NF;
     if (rows * 2 > 0x7fffffff) return fail(1, "batch too large for one call; split it (l2h_embed_max_batch)");
-    if (!e->attrs) {
-        CK(configure_rows_gemm());
+    int cur_dev = -1;
+    CK(cudaGetDevice(&cur_dev));
+    if (cur_dev != e->device)
+        return fail(1, "this handle's weights live on device " + std::to_string(e->device) + ", device " + std::to_string(cur_dev) +
+                       " is current: commit the weights again there (EmbedTFGridNet.to(device) does)");
+    if (e->attrs_dev != cur_dev) {
         CK(configure_lstm());
+        CK(umma::configure());
         CK(cudaFuncSetAttribute(eattn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EAOUT_SMEM));
-        e->attrs = true;
+        e->attrs_dev = cur_dev;
     }
     float* INV = wsp + ws.INV; double* GN = reinterpret_cast<double*>(wsp + ws.GN);
-    float* X = wsp + ws.X; float* A = wsp + ws.A; float* GX = wsp + ws.GX; float* HC = wsp + ws.HC;
-    float* QKV = wsp + ws.QKV; float* QN = wsp + ws.QN; float* KN = wsp + ws.KN; float* VN = wsp + ws.VN;
+    float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* HC = wsp + ws.HC;
+    float* QKV = wsp + ws.QKV; float* QN = wsp + ws.QN;
+    __nv_bfloat16* KP = reinterpret_cast<__nv_bfloat16*>(wsp + ws.KP);
+    __nv_bfloat16* VP = reinterpret_cast<__nv_bfloat16*>(wsp + ws.VP);
     float* S = wsp + ws.S; float* O = wsp + ws.O; float* HD = wsp + ws.HD;
+    const int Z = B * NH;
+    const int64_t k_plane = (int64_t)Z * Tp * QK, v_plane = (int64_t)Z * Tp * VDIM;
+    const int passes = e->passes;
 
     estd_kernel<<<B, 256, 0, st>>>(x, (int64_t)2 * N, INV);
     CK(cudaGetLastError());
@@ -287,8 +337,6 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
         egn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(X, GN, per_b, total4, e->w);
         CK(cudaGetLastError());
     }
-    // K/V padding rows (T..Tp-1) must be finite zeros for the padded P.V product
-    CK(cudaMemsetAsync(VN, 0, sizeof(float) * (size_t)B * NH * Tp * VDIM, st));
 
     for (int blk = 0; blk < e->n_blocks; ++blk) {
         const EmbBlockWeights& W = e->bw[blk];
@@ -297,56 +345,89 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
             const int Ls = inter ? T : NF;               // positions per sequence
             const int steps = Ls - KS + 1;
             const int nseq = inter ? B * NF : B * T;
-            ln_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(X, A, inter ? W.ln2_g : W.ln1_g,
-                                                                        inter ? W.ln2_b : W.ln1_b, rows, T, NF, inter ? 1 : 0);
-            CK(cudaGetLastError());
-            GemmArgs g{};
-            g.A = A; g.lda = 64; g.a_rows_per_seq = steps; g.a_seq_stride = (int64_t)Ls * 64;
-            g.Wt = inter ? W.wih2_t : W.wih1_t; g.bias = inter ? W.b2 : W.b1; g.C = GX; g.ldc = 512;
-            g.M = nseq * steps; g.N = 512; g.K = 256;
-            CK(launch_rows_gemm(g, st));
-            const int pad_rows = steps + 6;              // 3 zero rows either side of every sequence
-            CK(cudaMemsetAsync(HC, 0, sizeof(float) * (size_t)nseq * pad_rows * 128, st));
-            LstmArgs l{};
-            l.gx = GX; l.gx_ld = 512; l.out = HC + 3 * 128; l.out_ld = 128; l.whh = inter ? W.whh2 : W.whh1;
-            l.nseq = nseq; l.L = steps; l.inner_count = 1; l.outer_stride = steps; l.inner_stride = 0; l.step_stride = 1;
-            l.out_outer_stride = pad_rows; l.out_inner_stride = 0; l.out_step_stride = 1; l.ndir = 2;
-            CK(launch_lstm_rec(l, st));
-            g = GemmArgs{};                               // ConvTranspose1d(128->64, k=4) as a windowed GEMM + residual
-            g.A = HC; g.lda = 128; g.a_rows_per_seq = Ls; g.a_seq_stride = (int64_t)pad_rows * 128;
-            g.Wt = inter ? W.wl2_t : W.wl1_t; g.bias = inter ? W.bl2 : W.bl1; g.M = nseq * Ls; g.N = 64; g.K = 512;
-            g.C = X; g.R = X;
-            if (!inter) {
-                g.ldc = 64;                               // row (b,t,p=f) -> plain
-            } else {                                      // row ((b,f), p=t) -> X[b][t][f]
-                g.c_rows_per_seq = T; g.ldc = (int64_t)NF * 64; g.c_inner = NF; g.c_seq_stride = (int64_t)T * NF * 64;
-                g.c_inner_stride = 64;
+            // ---- LN + unfold(ks=4) + W_ih of both directions: one tensor-core GEMM.  Rows = (sequence, window start);
+            // the four taps are four k-chunks read at position offsets 0..3 of X itself (no unfolded copy, no LN pass,
+            // no transposed copy for the inter path: the tensor map strides do it) --------------------------------------
+            umma::GemmDesc g;
+            g.a0.base = X; g.a0.channels = 64;
+            if (!inter) { g.a0.n_pos = NF; g.a0.pos_stride = 64; g.a0.n_inner = nseq; g.a0.inner_stride = (int64_t)NF * 64; }
+            else {
+                g.a0.n_pos = T; g.a0.pos_stride = (int64_t)NF * 64; g.a0.n_inner = NF; g.a0.inner_stride = 64;
+                g.a0.n_outer = B; g.a0.outer_stride = (int64_t)T * NF * 64;
             }
-            CK(launch_rows_gemm(g, st));
+            umma::set_window_chunks(g, 64, KS, true);
+            g.ln_g = inter ? W.ln2_g : W.ln1_g; g.ln_b = inter ? W.ln2_b : W.ln1_b;
+            g.rows_per_seq = steps; g.nseq = nseq;
+            g.b = wplanes(e, inter ? W.wih2_t : W.wih1_t, 256, 512); g.N = 512; g.K = 256; g.passes = passes;
+            g.bias = inter ? W.b2 : W.b1; g.C = GX; g.ldc = 512; g.c_seq_stride = (int64_t)steps * 512;
+            CKU(umma::launch(g, st, &_why));
+            LstmArgs l{};
+            l.gx = GX; l.gx_ld = 512; l.out = HC; l.out_ld = 128; l.whh = inter ? W.whh2 : W.whh1;
+            l.nseq = nseq; l.L = steps; l.inner_count = 1; l.outer_stride = steps; l.inner_stride = 0; l.step_stride = 1;
+            l.ndir = 2;
+            CK(launch_lstm_rec(l, st));
+            // ---- ConvTranspose1d(128->64, k=4) + residual: output position p reads h rows p-3 .. p; rows outside the
+            // sequence are the zero-filled halo of the tensor map ----------------------------------------------------
+            umma::GemmDesc c;
+            c.a0.base = HC; c.a0.channels = 128; c.a0.n_pos = steps; c.a0.pos_stride = 128;
+            if (!inter) { c.a0.n_inner = nseq; c.a0.inner_stride = (int64_t)steps * 128; }
+            else { c.a0.n_inner = NF; c.a0.inner_stride = (int64_t)steps * 128; c.a0.n_outer = B; c.a0.outer_stride = (int64_t)NF * steps * 128; }
+            umma::set_window_chunks(c, 128, KS, false);
+            c.pos_bias = -(KS - 1);
+            c.rows_per_seq = Ls; c.nseq = nseq;
+            c.b = wplanes(e, inter ? W.wl2_t : W.wl1_t, 512, 64); c.N = 64; c.K = 512; c.passes = passes;
+            c.bias = inter ? W.bl2 : W.bl1; c.C = X; c.R = X;
+            if (!inter) { c.ldc = 64; c.c_seq_stride = (int64_t)NF * 64; }                 // row ((b,t), f) -> X[b][t][f]
+            else { c.ldc = (int64_t)NF * 64; c.c_inner = NF; c.c_seq_stride = (int64_t)T * NF * 64; c.c_inner_stride = 64; }   // ((b,f), t)
+            CKU(umma::launch(c, st, &_why));
         }
         // ---- full self-attention over frames ------------------------------------------------
-        GemmArgs g{};
-        g.A = X; g.lda = 64; g.Wt = W.wqkv_t; g.bias = W.bqkv; g.prelu_vec = W.slope_qkv; g.C = QKV; g.ldc = NQKV;
-        g.M = (int)rows; g.N = NQKV; g.K = 64;
-        CK(launch_rows_gemm(g, st));
-        eqkv_ln_kernel<<<dim3(T, B), 384, 0, st>>>(QKV, QN, KN, VN, W, T, Tp);
+        {
+            umma::GemmDesc g;                          // Q|K|V 1x1 convs of all heads + PReLU
+            g.a0.base = X; g.a0.channels = 64; g.a0.n_pos = rows; g.a0.pos_stride = 64;
+            umma::set_plain_chunks(g, 64);
+            g.rows_per_seq = (int)rows; g.nseq = 1;
+            g.b = wplanes(e, W.wqkv_t, 64, NQKV); g.N = NQKV; g.K = 64; g.passes = passes;
+            g.bias = W.bqkv; g.prelu_vec = W.slope_qkv; g.C = QKV; g.ldc = NQKV; g.c_seq_stride = 0;
+            CKU(umma::launch(g, st, &_why));
+        }
+        eqkv_ln_kernel<<<dim3(T, B), 384, 0, st>>>(QKV, QN, KP, VP, k_plane, v_plane, W, T, Tp);
         CK(cudaGetLastError());
-        const int Z = B * NH;
-        bgemm_kernel<true><<<dim3((T + 63) / 64, (T + 63) / 64, Z), 256, 0, st>>>(
-            QN, QK, (int64_t)Tp * QK, KN, QK, (int64_t)Tp * QK, S, Tp, (int64_t)T * Tp, T, T, QK, 1.f / sqrtf((float)QK));
-        CK(cudaGetLastError());
+        {
+            umma::GemmDesc g;                          // S = Q K^T / sqrt(520), per (utterance, head)
+            g.a0.base = QN; g.a0.channels = QK; g.a0.n_pos = T; g.a0.pos_stride = QK; g.a0.n_inner = Z; g.a0.inner_stride = (int64_t)Tp * QK;
+            umma::set_plain_chunks(g, QK);
+            g.rows_per_seq = T; g.nseq = Z; g.b_by_seq = true;
+            g.b.base = KP; g.b.ld = QK; g.b.z_stride = (int64_t)Tp * QK; g.b.plane_stride = k_plane; g.b.nz = Z;
+            g.N = T; g.K = QK; g.passes = passes; g.alpha = 1.f / sqrtf((float)QK);
+            g.C = S; g.ldc = Tp; g.c_seq_stride = (int64_t)T * Tp;
+            CKU(umma::launch(g, st, &_why));
+        }
         softmax_rows_kernel<<<(unsigned)((int64_t)Z * T), 128, 0, st>>>(S, Tp, T, T, (int64_t)T * Tp);
         CK(cudaGetLastError());
-        bgemm_kernel<false><<<dim3((VDIM + 63) / 64, (T + 63) / 64, Z), 256, 0, st>>>(
-            S, Tp, (int64_t)T * Tp, VN, VDIM, (int64_t)Tp * VDIM, O, VDIM, (int64_t)Tp * VDIM, T, VDIM, Tp, 1.f);
-        CK(cudaGetLastError());
+        {
+            umma::GemmDesc g;                          // O = P V (V is the MN-major B operand: [frame][f*16+c])
+            g.a0.base = S; g.a0.channels = T; g.a0.n_pos = T; g.a0.pos_stride = Tp; g.a0.n_inner = Z; g.a0.inner_stride = (int64_t)T * Tp;
+            umma::set_plain_chunks(g, T);
+            g.rows_per_seq = T; g.nseq = Z; g.b_by_seq = true;
+            g.b.base = VP; g.b.ld = VDIM; g.b.z_stride = (int64_t)Tp * VDIM; g.b.plane_stride = v_plane; g.b.nz = Z; g.b.mn_major = true;
+            g.N = VDIM; g.K = T; g.passes = passes;
+            g.C = O; g.ldc = VDIM; g.c_seq_stride = (int64_t)Tp * VDIM;
+            CKU(umma::launch(g, st, &_why));
+        }
         eattn_out_kernel<<<dim3(T, B), 256, EAOUT_SMEM, st>>>(O, X, W, T, Tp);
         CK(cudaGetLastError());
     }
     // ---- head: Linear(4160 -> 256) over rows (b,t) [features f*64+c], LN, mean over T -----------
-    GemmArgs g{};
-    g.A = X; g.lda = FC; g.Wt = e->w.wh_t; g.bias = e->w.bh; g.C = HD; g.ldc = 256; g.M = B * T; g.N = 256; g.K = FC;
-    CK(launch_rows_gemm(g, st));
+    {
+        umma::GemmDesc g;
+        g.a0.base = X; g.a0.channels = FC; g.a0.n_pos = (int64_t)B * T; g.a0.pos_stride = FC;
+        umma::set_plain_chunks(g, FC);
+        g.rows_per_seq = B * T; g.nseq = 1;
+        g.b = wplanes(e, e->w.wh_t, FC, 256); g.N = 256; g.K = FC; g.passes = passes;
+        g.bias = e->w.bh; g.C = HD; g.ldc = 256;
+        CKU(umma::launch(g, st, &_why));
+    }
     ehead_kernel<<<B, 256, 0, st>>>(HD, out, e->w, T);
     CK(cudaGetLastError());
     return 0;
@@ -376,6 +457,7 @@ int l2h_embed_destroy(void* handle) {
     EmbedEngine* e = static_cast<EmbedEngine*>(handle);
     if (!e) return 0;
     if (e->dev) cudaFree(e->dev);
+    if (e->planes) cudaFree(e->planes);
     delete e;
     return 0;
 }
@@ -414,12 +496,31 @@ int l2h_embed_commit_weights(void* handle, void* stream) {
     for (auto& kv : e->slots)
         if (kv.second.accumulate) kv.second.repack(kv.second.raw.data(), e->host.data());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (e->dev != nullptr && e->device != cur) return fail(1, "an enrollment handle is bound to the device of its first commit; create one handle per device");
     const bool first = e->dev == nullptr;
-    if (first) CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
+    if (first) {
+        CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
+        CK(cudaMalloc(&e->planes, 2 * e->planes_total * sizeof(__nv_bfloat16)));
+        e->device = cur;
+    }
     CK(cudaMemcpyAsync(e->dev, e->host.data(), e->total * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (const auto& ps : e->plane_srcs)        // k-major fp32 [K][N] -> bf16 hi/lo planes [N][K]
+        CK(umma::split_planes(e->dev + ps.wt_off, 1, ps.N, ps.N, ps.K, ps.K, e->planes + ps.plane_off,
+                              e->planes + e->planes_total + ps.plane_off, st));
     CK(cudaStreamSynchronize(st));
     if (first) resolve(e);
     e->committed = true;
+    return 0;
+}
+
+int l2h_embed_set_option(void* handle, const char* name, int32_t value) {
+    EmbedEngine* e = static_cast<EmbedEngine*>(handle);
+    if (!e || !name) return fail(1, "bad argument");
+    const std::string n(name);
+    if (n == "bf16") e->passes = value ? 1 : 3;      // 1: plain bf16 tensor-core operands; 0 (default): bf16x3 split, fp32-grade
+    else return fail(2, "unknown option: " + n);
     return 0;
 }
 

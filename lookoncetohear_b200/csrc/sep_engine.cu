@@ -16,6 +16,7 @@
 
 #include "../../include/lookonce_b200.h"
 #include "gemm.cuh"
+#include "umma_host.cuh"
 #include "lstm.cuh"
 #include "sep_kernels.cuh"
 #include "mid_kernel.cuh"
@@ -52,6 +53,14 @@ struct SepEngine {
     int device = -1;                // ordinal of the device that owns `dev`, the streams, events and cached graphs
     int64_t weight_gen = 0;         // bumped by every commit
     bool graph_stats = false;
+    // tensor-core path: bf16 hi/lo planes [2][N][K] of the GEMM weights, built on the device at commit
+    struct PlaneSrc { int64_t wt_off; int K, N, ld, col0; int64_t plane_off; };
+    std::vector<PlaneSrc> plane_srcs;
+    std::vector<int64_t> plane_of;      // per block: plane offsets of wih1, wl1, wih2, wl2, wqkv, [wih2|whh2]
+    __nv_bfloat16* planes = nullptr;
+    int64_t planes_total = 0;
+    bool use_tc = true;                 // rows > TC_MIN_ROWS: dense contractions on tcgen05 (option "tensor_cores")
+    int tc_passes = 3;                  // 3 = bf16x3 split products (fp32 configs); 1 = plain bf16 operands (option "bf16")
     int64_t total = 0;
     std::map<std::string, Slot> slots;
     SepWeights w;
@@ -65,7 +74,7 @@ struct SepEngine {
     int trace_cap = 0;
     int64_t launch_count = 0;                       // kernels launched so far (graph replays counted by their kernel nodes)
     cudaStream_t cap_stream = nullptr;
-    struct MidSrc { int64_t wl1, wih2, whh2t, wl2, wqkv, dst; };
+    struct MidSrc { int64_t wl1, wih2, whh2t, wl2, wqkv, dst, slopes, slope_vec; };
     std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
     cudaStream_t pipe_streams[128] = {};
     std::vector<cudaEvent_t> pipe_events;
@@ -203,9 +212,23 @@ static void build_layout(SepEngine* e) {
         proj("attn_conv_K", NHEAD * QE, NHEAD * QE, 1);
         proj("attn_conv_V", NHEAD * VD, 2 * NHEAD * QE, 2);
         bind(&W.wqkv_t, wqkv); bind(&W.bqkv, bqkv); bind(&W.slopes, slopes);
+        const int64_t slope_vec = alloc(NQKV);
+        bind(&W.slope_vec, slope_vec);
         const int64_t midp = alloc(MID_PACK);
         bind(&W.mid_pack, midp);
-        e->mid_src.push_back({wl1, wih2, whh2t, wl2, wqkv, midp});
+        e->mid_src.push_back({wl1, wih2, whh2t, wl2, wqkv, midp, slopes, slope_vec});
+        {   // tensor-core B operands of this block (offsets into the packed fp32 buffer; planes are made at commit)
+            auto reg = [&](int64_t wt, int K, int N, int ld, int col0, int64_t at) {
+                e->plane_srcs.push_back({wt, K, N, ld, col0, at});
+            };
+            auto take = [&](int K, int N) { const int64_t o = e->planes_total; e->planes_total += ((int64_t)K * N + 63) & ~int64_t(63); return o; };
+            const int64_t p_ih1 = take(64, 512), p_l1 = take(128, 64), p_ih2 = take(64, 256), p_l2 = take(64, 64), p_qkv = take(64, NQKV),
+                          p_cat = take(128, 256);
+            reg(wih1, 64, 512, 64, 0, p_ih1); reg(wl1, 128, 64, 128, 0, p_l1); reg(wih2, 64, 256, 64, 0, p_ih2);
+            reg(wl2, 64, 64, 64, 0, p_l2); reg(wqkv, 64, NQKV, 64, 0, p_qkv);
+            reg(wih2, 64, 256, 128, 0, p_cat); reg(whh2t, 64, 256, 128, 64, p_cat);      // [W_ih | W_hh]: k = [x | h]
+            for (int64_t v : {p_ih1, p_l1, p_ih2, p_l2, p_qkv, p_cat}) e->plane_of.push_back(v);
+        }
         bind(&W.lnq_g, plain(B + "attn_conv_Q.3.norm.weight", QK_DIM));
         bind(&W.lnq_b, plain(B + "attn_conv_Q.3.norm.bias", QK_DIM));
         bind(&W.lnk_g, plain(B + "attn_conv_K.3.norm.weight", QK_DIM));
@@ -237,7 +260,7 @@ static void shift_pointers(SepEngine* e, const float* new_base, const float* old
     for (auto& W : e->bw) {
         fixp(W.ln1_g); fixp(W.ln1_b); fixp(W.wih1_t); fixp(W.b1); fixp(W.whh1); fixp(W.wl1_t); fixp(W.bl1);
         fixp(W.ln2_g); fixp(W.ln2_b); fixp(W.wih2_t); fixp(W.b2); fixp(W.whh2); fixp(W.whh2_t); fixp(W.mid_pack); fixp(W.wl2_t); fixp(W.bl2);
-        fixp(W.wqkv_t); fixp(W.bqkv); fixp(W.slopes); fixp(W.lnq_g); fixp(W.lnq_b); fixp(W.lnk_g);
+        fixp(W.wqkv_t); fixp(W.bqkv); fixp(W.slopes); fixp(W.slope_vec); fixp(W.lnq_g); fixp(W.lnq_b); fixp(W.lnk_g);
         fixp(W.lnk_b); fixp(W.lnv_g); fixp(W.lnv_b); fixp(W.wp_t); fixp(W.bp); fixp(W.lnp_g); fixp(W.lnp_b);
     }
 }
@@ -265,7 +288,7 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.KALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * QK_LD : 0);
     ws.VALL = alloc(T > 1 ? (int64_t)B * NHEAD * (ATT - 1 + T) * V_DIM : 0);
     ws.PRE = alloc((int64_t)B * FC);
-    ws.QKVRAW = alloc(T == 1 ? (int64_t)B * NF * NQKV : 0);
+    ws.QKVRAW = alloc(rows * NQKV);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
     ws.total = cur;
     return ws;
@@ -298,7 +321,36 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(mid_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_C_SMEM));
     CK(configure_rows_gemm());
     CK(configure_lstm());
+    CK(umma::configure());
     g_attr_done[dev_ord] = true;
+    return 0;
+}
+
+
+// ---- dense contractions on the tensor cores (csrc/umma_gemm.cuh) for calls with many rows --------------------------
+constexpr int64_t TC_MIN_ROWS = 2048;      // below this the 16-row CUDA-core tiles win (one streaming frame = 97 rows)
+enum { PL_IH1 = 0, PL_L1, PL_IH2, PL_L2, PL_QKV, PL_CAT, PL_PER_BLOCK };
+
+static umma::BPlanes tc_planes(const SepEngine* e, int blk, int which, int ld) {
+    umma::BPlanes b;
+    b.base = e->planes + e->plane_of[(size_t)blk * PL_PER_BLOCK + which];
+    b.ld = ld; b.plane_stride = e->planes_total; b.nz = 1;
+    return b;
+}
+
+// C[rows][N] = epi(LN?(A[rows][lda, first K]) W^T + bias) (+ R), plain row-major rows
+static int tc_rows_gemm(SepEngine* e, int blk, int which, const float* A, int64_t lda, int K, int N, const float* ln_g, const float* ln_b,
+                        const float* bias, const float* prelu_vec, const float* R, float* C, int64_t ldc, int64_t rows, cudaStream_t st) {
+    umma::GemmDesc g;
+    g.a0.base = A; g.a0.channels = K; g.a0.n_pos = rows; g.a0.pos_stride = lda;
+    umma::set_plain_chunks(g, K, ln_g != nullptr);
+    g.ln_g = ln_g; g.ln_b = ln_b;
+    g.rows_per_seq = (int)rows; g.nseq = 1;
+    g.b = tc_planes(e, blk, which, K); g.N = N; g.K = K; g.passes = e->tc_passes;
+    g.bias = bias; g.prelu_vec = prelu_vec; g.R = R; g.C = C; g.ldc = ldc;
+    std::string why;
+    const cudaError_t ce = umma::launch(g, st, &why);
+    if (ce != cudaSuccess) return fail(3, std::string("umma_gemm: ") + cudaGetErrorString(ce) + " " + why);
     return 0;
 }
 
@@ -343,6 +395,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     // one-frame calls: the row-local middle of every block runs as ONE fused kernel (mid_kernel.cuh).
     // (Taps want the intermediate activations of the generic chain, so they keep it.)
     const bool fused_mid = (T == 1) && e->use_mid && !(flags & L2H_FLAG_TAPS);
+    // many rows (whole utterances, offline batches, many streams): the dense contractions run on the tensor cores
+    const bool tc = e->use_tc && rows > TC_MIN_ROWS;
+    const bool tc_mid = tc && T == 1 && !(flags & L2H_FLAG_TAPS);
     int tap = 0;
     auto do_tap = [&]() -> int {
         if (flags & L2H_FLAG_TAPS) {
@@ -364,9 +419,13 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         const BlockWeights& W = e->bw[b];
         // ---- intra: LN -> W_ih (both directions) -> BiLSTM over F -> Linear -> +res ------------
         GemmArgs g{};
-        g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
-        g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
-        CK(launch_rows_gemm(g, st, pdl));
+        if (tc) {
+            if (int rc = tc_rows_gemm(e, b, PL_IH1, X, 64, 64, 512, W.ln1_g, W.ln1_b, W.b1, nullptr, nullptr, GX, 512, rows, st)) return rc;
+        } else {
+            g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
+            g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
+            CK(launch_rows_gemm(g, st, pdl));
+        }
         MARK("gemm_ih_intra");
         LstmArgs l{};
         l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
@@ -374,7 +433,32 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         l.ndir = 2;
         CK(launch_lstm_rec(l, st, pdl));
         MARK("lstm_intra");
-        if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
+        if (tc_mid) {
+            // many streams, one hop: the row-local middle of the block as four tensor-core GEMMs and the cell update.
+            // The inter-LSTM step is ONE GEMM over the concatenated k = [LN(x) | h_prev] (h read in place from the
+            // per-stream state records through a strided tensor map) against [W_ih | W_hh].
+            if (int rc = tc_rows_gemm(e, b, PL_L1, Y, 128, 128, 64, nullptr, nullptr, W.bl1, nullptr, X, X, 64, rows, st)) return rc;
+            {
+                umma::GemmDesc q;
+                q.a0.base = X; q.a0.channels = 64; q.a0.n_pos = NF; q.a0.pos_stride = 64; q.a0.n_inner = B; q.a0.inner_stride = (int64_t)NF * 64;
+                q.a1.base = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
+                q.a1.channels = 64; q.a1.n_pos = NF; q.a1.pos_stride = 64; q.a1.n_inner = B; q.a1.inner_stride = ss;
+                q.n_chunks = 2;
+                q.chunks[0].c0 = 0; q.chunks[0].dp = 0; q.chunks[0].flags = 2;      // x: LayerNorm
+                q.chunks[1].c0 = 0; q.chunks[1].dp = 0; q.chunks[1].flags = 1;      // h: second source
+                q.ln_g = W.ln2_g; q.ln_b = W.ln2_b;
+                q.rows_per_seq = NF; q.nseq = B;
+                q.b = tc_planes(e, b, PL_CAT, 128); q.N = 256; q.K = 128; q.passes = e->tc_passes;
+                q.bias = W.b2; q.C = GX; q.ldc = 256; q.c_seq_stride = (int64_t)NF * 256;
+                std::string why;
+                const cudaError_t ce = umma::launch(q, st, &why);
+                if (ce != cudaSuccess) return fail(3, std::string("umma_gemm (inter step): ") + cudaGetErrorString(ce) + " " + why);
+            }
+            CK(launch_k(false, lstm_cell_rows_kernel, dim3((unsigned)((rows * 64 + 255) / 256)), dim3(256), 0, st, (const float*)GX, state, ss, b, Y, (int)rows));
+            if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
+            if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
+            MARK("mid");
+        } else if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
             float* GI = GX; float* HN = GX + rows * 256;         // the BiLSTM is done with GX
             CK(launch_k(pdl, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st, (const float*)Y, X, GI, W, B));
             if (e->fold_mid_c) {
@@ -391,17 +475,25 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                 CK(launch_k(pdl, mid_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
             MARK("mid");
         } else {
-        g = GemmArgs{};
-            g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
-            g.M = (int)rows; g.N = 64; g.K = 128;
-            CK(launch_rows_gemm(g, st, pdl));
+            if (tc) {
+                if (int rc = tc_rows_gemm(e, b, PL_L1, Y, 128, 128, 64, nullptr, nullptr, W.bl1, nullptr, X, X, 64, rows, st)) return rc;
+            } else {
+                g = GemmArgs{};
+                g.A = Y; g.lda = 128; g.Wt = W.wl1_t; g.bias = W.bl1; g.C = X; g.ldc = 64; g.R = X;
+                g.M = (int)rows; g.N = 64; g.K = 128;
+                CK(launch_rows_gemm(g, st, pdl));
+            }
             MARK("gemm_lin_intra");
             if (int rc = do_tap()) return rc;
             // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
-            g = GemmArgs{};
-            g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
-            g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
-            CK(launch_rows_gemm(g, st, pdl));
+            if (tc) {
+                if (int rc = tc_rows_gemm(e, b, PL_IH2, X, 64, 64, 256, W.ln2_g, W.ln2_b, W.b2, nullptr, nullptr, GX, 256, rows, st)) return rc;
+            } else {
+                g = GemmArgs{};
+                g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
+                g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
+                CK(launch_rows_gemm(g, st, pdl));
+            }
             MARK("gemm_ih_inter");
             l = LstmArgs{};
             l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
@@ -412,10 +504,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             l.step_stride = NF; l.ndir = 1;
             CK(launch_lstm_rec(l, st, pdl));
             MARK("lstm_inter");
-            g = GemmArgs{};
-            g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
-            g.M = (int)rows; g.N = 64; g.K = 64;
-            CK(launch_rows_gemm(g, st, pdl));
+            if (tc) {
+                if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
+            } else {
+                g = GemmArgs{};
+                g.A = Y; g.lda = 64; g.Wt = W.wl2_t; g.bias = W.bl2; g.C = X; g.ldc = 64; g.R = X;
+                g.M = (int)rows; g.N = 64; g.K = 64;
+                CK(launch_rows_gemm(g, st, pdl));
+            }
             MARK("gemm_lin_inter");
             if (int rc = do_tap()) return rc;
         }
@@ -425,8 +521,11 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                         VALL, T));
             MARK("kv_gather");
         }
+        if (tc && !tc_mid) {      // Q|K|V projections of all rows as one tensor-core GEMM (+ bias + PReLU per column)
+            if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
+        }
         CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
-                    (const float*)((fused_mid && !e->fold_mid_c) ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
+                    (const float*)((tc || (fused_mid && !e->fold_mid_c)) ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
         MARK("qkv");
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
@@ -734,10 +833,10 @@ static int run_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t st
 // stream the first time this exact argument set is seen; graph launches go to the caller's stream).
 static int run_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st, bool use_graph) {
     if (!use_graph || (a.flags & L2H_FLAG_TAPS)) {
-        int32_t n = 0;
-        l2h_sep_launches_per_forward(e, a.T, &n);
-        e->launch_count += n;
-        return enqueue_chain(e, a, st);
+        const long long before = g_launches;
+        const int rc = enqueue_chain(e, a, st);
+        e->launch_count += g_launches - before;
+        return rc;
     }
     std::vector<int64_t> key = {(int64_t)a.x, a.xbs, a.xcs, a.x_len, (int64_t)a.emb, (int64_t)a.state, (int64_t)a.y,
                                 a.ybs, a.ycs, a.y_len, a.B, a.T, (int64_t)a.wsp, (int64_t)a.flags, a.pos_rel};
@@ -807,6 +906,7 @@ static void release_device_resources(SepEngine* e) {
     e->pipe_events.clear();
     if (e->trace_dev) { cudaFree(e->trace_dev); e->trace_dev = nullptr; e->trace_cap = 0; }
     if (e->dev) { cudaFree(e->dev); e->dev = nullptr; }
+    if (e->planes) { cudaFree(e->planes); e->planes = nullptr; }
     if (sw) cudaSetDevice(cur);
 }
 
@@ -872,6 +972,8 @@ int l2h_sep_commit_weights(void* handle, void* stream) {
         if (kv.second.accumulate) std::fill(e->host.begin() + kv.second.off, e->host.begin() + kv.second.off + 256, 0.f);
     for (auto& kv : e->slots)
         if (kv.second.accumulate) kv.second.repack(kv.second.raw.data(), e->host.data());
+    for (const auto& m : e->mid_src)        // per-column PReLU slopes of the fused Q|K|V projection
+        for (int n = 0; n < NQKV; ++n) e->host[m.slope_vec + n] = e->host[m.slopes + (n < NHEAD * QE ? 0 : (n < 2 * NHEAD * QE ? 1 : 2))];
     for (const auto& m : e->mid_src) {      // k-sliced, bank-padded copies for mid_kernel (layout: mid_kernel.cuh)
         float* h = e->host.data();
         std::fill(h + m.dst, h + m.dst + MID_PACK, 0.f);
@@ -898,8 +1000,12 @@ int l2h_sep_commit_weights(void* handle, void* stream) {
         CK(cudaMalloc(&e->dev, e->total * sizeof(float)));
         e->device = cur;
         shift_pointers(e, e->dev, old_base);
+        CK(cudaMalloc(&e->planes, 2 * e->planes_total * sizeof(__nv_bfloat16)));
     }
     CK(cudaMemcpyAsync(e->dev, e->host.data(), e->total * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (const auto& ps : e->plane_srcs)        // k-major fp32 [K][N] -> bf16 hi/lo planes [N][ld] (tensor-core B operands)
+        CK(umma::split_planes(e->dev + ps.wt_off, 1, ps.N, ps.N, ps.K, ps.ld, e->planes + ps.plane_off + ps.col0,
+                              e->planes + e->planes_total + ps.plane_off + ps.col0, st));
     CK(cudaStreamSynchronize(st));
     e->committed = true;
     ++e->weight_gen;
@@ -1130,6 +1236,9 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "fused_mid") e->use_mid = value != 0;
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
+    else if (n == "tensor_cores") e->use_tc = value != 0;
+    else if (n == "bf16") e->tc_passes = value ? 1 : 3;
+    else if (n == "graph_stats") e->graph_stats = value != 0;
     else return fail(2, "unknown option: " + n);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting
     e->graphs.clear();

@@ -40,6 +40,7 @@ struct BlockWeights {
     const float* wqkv_t;              // [64][112]   cols: Q(h*6+e) | K(h*6+e) | V(h*16+c)
     const float* bqkv;                // [112]
     const float* slopes;              // [4]  PReLU of Q, K, V, proj
+    const float* slope_vec;           // [112] the Q/K/V slopes per projection column (epilogue of the tensor-core QKV GEMM)
     const float *lnq_g, *lnq_b;       // [582]
     const float *lnk_g, *lnk_b;       // [582]
     const float *lnv_g, *lnv_b;       // [1552]
@@ -1005,6 +1006,37 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
             __threadfence();
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// One inter-LSTM step for many streams, cell part only (tfgridnet_causal.py:524-532 with T = 1): the gate
+// pre-activations [rows][256] (column j*4+q, q in i,f,g,o; = LN(x) W_ih^T + h W_hh^T + b from ONE tensor-core GEMM
+// over the concatenated k = [x | h]) and the carried cell state give the new (h, c), written back to the per-stream
+// state records, and h again as contiguous rows for the Linear that follows.  One thread per (row, hidden unit).
+__global__ void __launch_bounds__(256)
+lstm_cell_rows_kernel(const float* __restrict__ gates, float* __restrict__ state, int64_t sstride, int blk, float* __restrict__ Hout,
+                      int rows) {
+    griddep_launch();
+    griddep_wait();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)rows * 64) return;
+    const int row = (int)(i >> 6), j = (int)(i & 63);
+    const int b = row / NF, f = row % NF;
+    const float4 g = *reinterpret_cast<const float4*>(gates + (int64_t)row * 256 + j * 4);
+    float* base = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+    float* hp = base + BK_H + f * 64 + j;
+    float* cp = base + BK_C + f * 64 + j;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float ig = __fdividef(1.f, 1.f + ex2_ftz(-LOG2E * g.x));
+    const float fg = __fdividef(1.f, 1.f + ex2_ftz(-LOG2E * g.y));
+    const float gg = __fdividef(2.f, 1.f + ex2_ftz(-2.f * LOG2E * g.z)) - 1.f;
+    const float og = __fdividef(1.f, 1.f + ex2_ftz(-LOG2E * g.w));
+    const float c = fg * *cp + ig * gg;
+    const float h = og * (__fdividef(2.f, 1.f + ex2_ftz(-2.f * LOG2E * c)) - 1.f);
+    *cp = c;
+    *hp = h;
+    Hout[i] = h;
 }
 
 }  // namespace l2h

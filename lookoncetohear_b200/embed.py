@@ -79,6 +79,15 @@ class EmbedTFGridNet(nn.Module):
     def refresh_weights(self):
         self._dirty = True
 
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_handle"], d["_ws"], d["_dirty"] = None, None, True
+        return d
+
+    def set_option(self, name, value):
+        """"bf16": 1 = plain bf16 tensor-core operands (one MMA pass), 0 = bf16x3 split products (default, fp32-grade)."""
+        _cabi.check(_cabi.lib().l2h_embed_set_option(self._engine(), name.encode(), int(value)))
+
     def __del__(self):
         try:
             if self._handle is not None:

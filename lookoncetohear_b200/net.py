@@ -94,16 +94,21 @@ class _TFGridNetParams(nn.Module):
 class SepState(dict):
     """The streaming state returned by ``Net.init_buffers`` and threaded through ``predict``.
 
-    One contiguous device allocation (header + per-stream records, layout in csrc/sep_layout.h)
-    that the kernels update in place; the dict interface is kept because reference callers treat
-    the state as an opaque dict they pass back.  ``to_reference()`` / ``load_reference()``
-    convert to/from the reference's nested dict of tensors (tfgridnet_causal.py:173-186,408-427).
+    One contiguous device allocation (header + per-stream records, layout in csrc/sep_layout.h,
+    exported through ``l2h_sep_state_offsets``) that the kernels update in place; the dict interface
+    is kept because reference callers treat the state as an opaque dict they pass back.
+    ``to_reference()`` / ``load_reference()`` convert to / from the reference's nested dict of
+    tensors (tfgridnet_causal.py:173-186, :408-427).
     """
 
-    def __init__(self, buf, batch, n_blocks, header_bytes, stride):
+    _OFFSET_NAMES = ("ring", "k_ld", "k_dim", "v_dim", "att", "st_emb", "st_gate", "st_conv", "st_deconv",
+                     "st_istft", "st_blk", "bk_k", "bk_v", "bk_h", "bk_c", "bk_stride")
+
+    def __init__(self, buf, batch, n_blocks, header_bytes, stride, offsets):
         super().__init__()
         self.buf, self.batch, self.n_blocks = buf, batch, n_blocks
         self.header_floats, self.stride = header_bytes // 4, stride
+        self.lay = dict(zip(self._OFFSET_NAMES, offsets))
         self["buf"] = buf
 
     # ---- views ------------------------------------------------------------------------------
@@ -115,43 +120,66 @@ class SepState(dict):
         h = self.buf[:4].view(torch.int64).cpu()
         return int(h[0]), int(h[1])
 
-    _F, _C, _ATT, _QKLD, _QK, _VD, _NH = 97, 64, 50, 584, 582, 1552, 4
-    _ST_GATE = 256
-    _ST_CONV = 256 + 6208
-    _ST_DECONV = _ST_CONV + 2 * 2 * 4 * 97
-    _ST_ISTFT = _ST_DECONV + 2 * 2 * 6208
-    _ST_BLK = _ST_ISTFT + 2 * 2 * 194
-    _RING = 56                      # K/V ring slots per head (csrc/sep_layout.h)
-    _BK_V = 4 * _RING * 584
-    _BK_H = _BK_V + 4 * _RING * 1552
-    _BK_C = _BK_H + 6208
-    _BK_STRIDE = _BK_C + 6208
+    def _tails(self, r, par):
+        L, B = self.lay, self.batch
+        conv = r[:, L["st_conv"]:L["st_deconv"]].view(B, 2, 2, 4, 97)[:, par]            # [B,slot,ch,F]
+        deconv = r[:, L["st_deconv"]:L["st_istft"]].view(B, 2, 2, 97, 64)[:, par]        # [B,slot,F,C]
+        istft = r[:, L["st_istft"]:L["st_blk"]].view(B, 2, 2, 194)[:, par]               # [B,ear,2F]
+        return conv, deconv, istft
+
+    def _block(self, r, i):
+        L, B = self.lay, self.batch
+        o = L["st_blk"] + i * L["bk_stride"]
+        K = r[:, o + L["bk_k"]:o + L["bk_v"]].view(B, 4, L["ring"], L["k_ld"])
+        V = r[:, o + L["bk_v"]:o + L["bk_h"]].view(B, 4, L["ring"], L["v_dim"])
+        h = r[:, o + L["bk_h"]:o + L["bk_c"]]
+        c = r[:, o + L["bk_c"]:o + L["bk_stride"]]
+        return K, V, h, c
 
     def to_reference(self):
         """Nested dict with the reference's keys and shapes (copies; synchronises)."""
         pos, ncalls = self.header()
-        par = ncalls & 1
-        r, B = self._rec(), self.batch
-        conv = r[:, self._ST_CONV:self._ST_DECONV].view(B, 2, 2, 4, 97)[:, par]            # [B,slot,ch,F]
-        deconv = r[:, self._ST_DECONV:self._ST_ISTFT].view(B, 2, 2, 97, 64)[:, par]        # [B,slot,F,C]
-        istft = r[:, self._ST_ISTFT:self._ST_BLK].view(B, 2, 2, 194)[:, par]               # [B,ear,2F]
+        L, r, B = self.lay, self._rec(), self.batch
+        hist = L["att"] - 1
+        conv, deconv, istft = self._tails(r, ncalls & 1)
         out = dict(conv_buf=conv.permute(0, 2, 1, 3).contiguous(),
                    deconv_buf=deconv.permute(0, 3, 1, 2).contiguous(),
                    istft_buf=istft.unsqueeze(-1).contiguous(), gridnet_bufs={})
-        # ring slot of frame n is n % RING; history rows are frames pos-49 .. pos-1
-        frames = torch.arange(pos - 49, pos)
-        slots = torch.remainder(frames, self._RING).to(self.buf.device)
+        # ring slot of frame n is n % ring; history rows are frames pos-49 .. pos-1
+        frames = torch.arange(pos - hist, pos)
+        slots = torch.remainder(frames, L["ring"]).to(self.buf.device)
         live = (frames >= 0).to(self.buf.device, self.buf.dtype)[None, None, :, None]
         for i in range(self.n_blocks):
-            o = self._ST_BLK + i * self._BK_STRIDE
-            K = r[:, o:o + self._BK_V].view(B, 4, self._RING, 584)[:, :, :, :582]
-            V = r[:, o + self._BK_V:o + self._BK_H].view(B, 4, self._RING, 1552)
+            K, V, h, c = self._block(r, i)
             out["gridnet_bufs"][f"buf{i}"] = dict(
-                K_buf=(K[:, :, slots] * live).reshape(B * 4, 49, 582).contiguous(),
-                V_buf=(V[:, :, slots] * live).reshape(B * 4, 49, 1552).contiguous(),
-                h0=r[:, o + self._BK_H:o + self._BK_C].reshape(1, B * 97, 64).clone(),
-                c0=r[:, o + self._BK_C:o + self._BK_STRIDE].reshape(1, B * 97, 64).clone())
+                K_buf=(K[:, :, slots, :L["k_dim"]] * live).reshape(B * 4, hist, L["k_dim"]).contiguous(),
+                V_buf=(V[:, :, slots] * live).reshape(B * 4, hist, L["v_dim"]).contiguous(),
+                h0=h.reshape(1, B * 97, 64).clone(), c0=c.reshape(1, B * 97, 64).clone())
         return out
+
+    def load_reference(self, ref_state):
+        """Import a state in the reference's format (the nested dict ``Net.init_buffers`` /
+        ``predict`` of the reference produce) so a stream started on the reference implementation can
+        be continued here.  The 49 history rows become frames 0..48 of the rings (pos = 49)."""
+        L, r, B = self.lay, self._rec(), self.batch
+        hist = L["att"] - 1
+        dev, dt = self.buf.device, self.buf.dtype
+        self.buf.zero_()
+        hdr = self.buf[:4].view(torch.int64)
+        hdr[0] = hist            # pos: frames consumed so far
+        hdr[1] = 0               # ncalls: tails live in parity slot 0
+        conv, deconv, istft = self._tails(r, 0)
+        conv.copy_(ref_state["conv_buf"].to(dev, dt).permute(0, 2, 1, 3))
+        deconv.copy_(ref_state["deconv_buf"].to(dev, dt).permute(0, 2, 3, 1))
+        istft.copy_(ref_state["istft_buf"].to(dev, dt)[..., 0])
+        for i in range(self.n_blocks):
+            K, V, h, c = self._block(r, i)
+            g = ref_state["gridnet_bufs"][f"buf{i}"]
+            K[:, :, :hist, :L["k_dim"]] = g["K_buf"].to(dev, dt).view(B, 4, hist, L["k_dim"])
+            V[:, :, :hist] = g["V_buf"].to(dev, dt).view(B, 4, hist, L["v_dim"])
+            h.copy_(g["h0"].to(dev, dt).reshape(B, 97 * 64))
+            c.copy_(g["c0"].to(dev, dt).reshape(B, 97 * 64))
+        return self
 
 
 class Net(nn.Module):
@@ -195,6 +223,20 @@ class Net(nn.Module):
     def refresh_weights(self):
         """Call after editing parameters in place; load_state_dict / .to() / .cuda() do it themselves."""
         self._dirty = True
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle: the native handle, workspace and staging buffers are per-instance
+        d = dict(self.__dict__)
+        d["_handle"], d["_ws"], d["_dirty"] = None, None, True
+        d.pop("_host_stage", None)
+        d.pop("_last_stream_state", None)
+        d["_cfg"] = bytes(self._cfg)
+        return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        d["_cfg"] = _cabi.SepConfig.from_buffer_copy(d["_cfg"])
+        self.__dict__.update(d)
 
     def _apply(self, fn, *args, **kwargs):
         self._dirty = True
@@ -267,13 +309,21 @@ class Net(nn.Module):
         L, h = _cabi.lib(), self._engine()
         n = ctypes.c_size_t()
         _cabi.check(L.l2h_sep_state_bytes(h, batch_size, ctypes.byref(n)))
-        hb, stride = ctypes.c_int64(), ctypes.c_int64()
-        _cabi.check(L.l2h_sep_state_layout(h, ctypes.byref(hb), ctypes.byref(stride)))
+        hb, stride, offs = self._state_layout()
         buf = torch.empty(n.value // 4, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             _cabi.check(L.l2h_sep_state_init(h, buf.data_ptr(), batch_size,
                                              torch.cuda.current_stream(device).cuda_stream))
-        return SepState(buf, batch_size, self.n_blocks, hb.value, stride.value)
+        return SepState(buf, batch_size, self.n_blocks, hb, stride, offs)
+
+    def _state_layout(self):
+        """(header bytes, floats per stream record, record offsets) from the C side."""
+        L, h = _cabi.lib(), self._engine()
+        hb, stride = ctypes.c_int64(), ctypes.c_int64()
+        _cabi.check(L.l2h_sep_state_layout(h, ctypes.byref(hb), ctypes.byref(stride)))
+        offs = (ctypes.c_int64 * 16)()
+        _cabi.check(L.l2h_sep_state_offsets(h, offs, 16))
+        return hb.value, stride.value, list(offs)
 
     def _run(self, x, embed, state, frames, out_len, flags=0):
         """x [B,M,n] (any length; samples beyond n read as zero), embed [B,256]."""

@@ -56,6 +56,12 @@ def main():
         emb = en(xe)
     np.savez_compressed(os.path.join(HERE, "embed_golden.npz"), seed=seed, n=4800, emb=emb.numpy(),
                         wsum=weight_checksum(en.state_dict()))
+    # ---- state_dict key names and shapes of both reference modules (checkpoint compatibility) ----
+    import json
+    keys = {"sep": {k: list(v.shape) for k, v in net.state_dict().items()},
+            "embed": {k: list(v.shape) for k, v in en.state_dict().items()}}
+    with open(os.path.join(HERE, "ckpt_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
     print("written", os.listdir(HERE))
 
 

@@ -139,3 +139,22 @@ def test_si_sdr_known_answer():
     n = n - (n * t).sum() / (t * t).sum() * t          # orthogonal noise
     p = 3.0 * t + 0.3 * n * (t.norm() / n.norm()) * 3.0
     assert abs(float(rs.si_sdr(p, t)) - 20 * np.log10(1 / 0.3)) < 1e-3
+
+
+@needs_ref
+def test_stft_shim_equals_the_stft_the_reference_vendors():
+    """The one piece of espnet2 arithmetic the reference DOES carry -- Stft.forward, src/models/tfgridnet_orig/
+    stft.py:68-195, identical to what espnet2's STFTEncoder calls -- pins the shim the enrollment oracle uses
+    (oracle/shims/espnet2/enh/encoder/stft_encoder.py): same frames, same bins, same values, same output lengths."""
+    import importlib
+    rl._prepare()
+    vendored = importlib.import_module("src.models.tfgridnet_orig.stft").Stft
+    from espnet2.enh.encoder.stft_encoder import STFTEncoder
+    for n_fft, hop, n in ((128, 64, 5000), (128, 64, 4999), (192, 128, 3001)):
+        x = synth.enrollment(3, n).transpose(1, 2).contiguous()          # [B, N, M] as EmbedTFGridNet.forward passes it
+        ilens = torch.tensor([n, n, n])
+        ref, rl_out = vendored(n_fft=n_fft, win_length=n_fft, hop_length=hop, window="hann")(x, ilens)     # [B,T,M,F,2]
+        got, gl_out = STFTEncoder(n_fft, n_fft, hop, window="hann")(x, ilens)                             # complex [B,T,M,F]
+        assert got.shape == ref.shape[:-1] and got.shape[1] == 1 + n // hop
+        assert torch.equal(rl_out, gl_out)
+        assert rs.rel_l2(torch.view_as_real(got), ref) < 1e-6

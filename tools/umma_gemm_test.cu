@@ -1,10 +1,11 @@
 // Standalone correctness + throughput harness for csrc/umma_gemm.cuh (tcgen05 / TMEM / tensor-map TMA GEMM).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/umma_gemm_test tools/umma_gemm_test.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/umma_gemm_test tools/umma_gemm_test.cu lookoncetohear_b200/csrc/umma_gemm.cu
 // Every case is checked against a double-precision CPU product of the same fp32 inputs.
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <vector>
 #include "../lookoncetohear_b200/csrc/umma_host.cuh"
@@ -147,6 +148,7 @@ static int run_case(const Case& c, bool timing = false) {
 
 int main(int argc, char** argv) {
     const bool perf = argc > 1 && atoi(argv[1]) != 0;
+    const char* only = argc > 2 ? argv[2] : nullptr;      // run only the cases whose name contains this
     int fails = 0;
     //            name                  nseq  Ls    C   w  rows  pb   N   ps  ln    bias  pvec  res   int   alpha bseq  mn    two   inner
     const Case cases[] = {
@@ -167,7 +169,7 @@ int main(int argc, char** argv) {
         {"two_src_k128_n256",           1,  1500,  64, 1, 1500, 0,  256, 3, true,  true,  false, false, false, 1.f, false, false, true,  0},
         {"k4160_n256",                  1,   600, 4160, 1, 600, 0,  256, 3, false, true,  false, false, false, 1.f, false, false, false, 0},
     };
-    for (const Case& c : cases) fails += run_case(c);
+    for (const Case& c : cases) if (!only || strstr(c.name, only)) fails += run_case(c);
     if (perf) {
         const Case pc[] = {
             {"perf_k64_n512_ln_p3",     1, 1 << 20,  64, 1, 1 << 20, 0, 512, 3, true,  true, false, false, false, 1.f, false, false, false, 0},
@@ -180,7 +182,7 @@ int main(int argc, char** argv) {
             {"perf_pv_k1280_n1040_p3",  32, 1251,  1280, 1, 1251,    0, 1040, 3, false, false, false, false, false, 1.f, true, true,  false, 0},
             {"perf_pv_k1280_n1040_p1",  32, 1251,  1280, 1, 1251,    0, 1040, 1, false, false, false, false, false, 1.f, true, true,  false, 0},
         };
-        for (const Case& c : pc) fails += run_case(c, true);
+        for (const Case& c : pc) if (!only || strstr(c.name, only)) fails += run_case(c, true);
     }
     printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL OK", fails);
     return fails ? 1 : 0;
