@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: separated frames/s (8 ms hops of a 16 kHz
-binaural stream) and the real-time factor, for BASELINE.json configs[1]: streaming separation,
-8 ms chunks, batch 1, fp32, one stream per GPU.
+binaural stream) and the real-time factor, for BASELINE.json configs[1]: separation in 8 ms chunks,
+batch 1, fp32, one stream per GPU.
 
-A *step* = one pass of the hot path over one synthetic 4 s binaural mixture (500 hops) per GPU,
-fed chunk by chunk through the streaming-state API with a fresh state (state init is inside the
-step).  `value` = hops/s over all ranks with the clip resident in HBM (l2h_sep_stream_dev);
-`e2e` = the same through the C-ABI host-buffer call (l2h_sep_stream_host): every chunk is copied
-host->device from pinned memory and its 128 output samples per ear copied back, inside the timed
-region.  `--impl reference` times the reference's own CPU path (the reference modules when the
-checkout is present, else the oracle port) on the host cores with the same workload.
+A *step* = one pass of the hot path over one synthetic 4 s binaural mixture (500 hops) per GPU with a
+fresh state (state init is inside the step).  Every hop is its own one-hop kernel chain with the
+streaming state carried hop to hop, but -- read this -- `value` is BUFFERED-CLIP THROUGHPUT: the whole
+clip is resident when the step starts and the 500 one-hop chains run as one wavefront-pipelined CUDA
+graph (hop t+1 starts before hop t has finished), which needs the future audio to be there already.
+The strictly causal figures (hop t+1 not started before hop t is out) are reported on the same line
+under `streaming_causal`: frames/s, real-time factor, single-chunk latency, and an end-to-end variant
+that copies every 8 ms chunk host->device and its output back per hop.
+`value` = hops/s over all ranks with the clip resident in HBM (l2h_sep_stream_dev); `e2e` = the same
+through the C-ABI host-buffer call (l2h_sep_stream_host): per round of up to 500 hops ONE host->device
+copy of the round's samples from pinned memory and ONE device->host copy of its output, inside the
+timed region.  Further blocks on the line: `batched_streaming` (configs[4] per-GPU shape, 256 streams
+per rank, at every N), `offline_bf16_256` (configs[2]), `enrollment_1024` (configs[3]).
+`--impl reference` times the reference's own CPU path (the reference modules when the checkout is
+present, else the oracle port) on the host cores with the same workload.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks-per-call C] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -32,7 +40,8 @@ import torch  # noqa: E402
 CLIP_SAMPLES = 64000          # 4 s @ 16 kHz (configs[0]/[1]: "single 4 s binaural mixture")
 HOP = 128
 FRAMES = CLIP_SAMPLES // HOP  # 500
-METRIC = "separated frames/sec (8 ms chunks, 16 kHz binaural, streaming, batch 1 per GPU)"
+METRIC = ("separated frames/sec (8 ms chunks, 16 kHz binaural, batch 1 per GPU): buffered-clip throughput, the one-hop chains "
+          "of a resident clip pipelined as a wavefront; strictly causal figures under streaming_causal")
 # algorithmic work per hop per stream
 FLOP_PER_FRAME = 74.67e6
 BYTES_PER_FRAME = 5.50e6
@@ -42,8 +51,8 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", 1412.4), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
@@ -137,6 +146,85 @@ def time_cpu_streaming(frames, chunks_per_call, passes, threads, seed=0):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     return frames / best, kind, best
+
+
+
+# FLOPs per hop per stream that run as tensor-core GEMMs in the batched / offline paths
+# (per block: W_ih of both LSTMs 6.36 + 3.18, the two Linears 1.59 + 0.79, Q|K|V 1.39 MFLOP) x 3 blocks
+TC_FLOP_PER_FRAME = 3 * (6.36 + 3.18 + 1.59 + 0.79 + 1.39) * 1e6
+EMBED_FLOP_PER_UTT = 255e9            # 5 s utterance, SURVEY.md section 2.1
+EMBED_TC_FLOP_PER_UTT = 255e9 - 31e9  # everything except the recurrent h W_hh products (CUDA cores)
+
+
+def _dev_time(fn, reps, sync):
+    """best-of-`reps` device time (ms) of fn() with CUDA events"""
+    best = None
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        sync()
+        ms = a.elapsed_time(b)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def measure_batched_streaming(net, dev, rank, nb=256, nsteps=60):
+    """BASELINE configs[4] per-GPU shape: `nb` independent streams advancing one 8 ms hop per step (this rank's
+    share of the 2048).  Returns (ms for nsteps-10 steps, state GB)."""
+    from lookoncetohear_b200 import synth
+    g = torch.Generator().manual_seed(5000 + rank)
+    xb = (0.1 * torch.randn(nb, 2, HOP * nsteps, generator=g)).to(dev)
+    eb = synth.embedding(8, seed0=6000 + rank)[:, 0].repeat(nb // 8, 1).to(dev)
+    yb = torch.empty(nb, 2, HOP * nsteps, device=dev)
+    best, stb = None, None
+    for it in range(3):
+        stb = net.init_buffers(nb, dev)
+        net.stream_dev(xb, eb, chunks_per_call=1, state=stb, n_calls=10, out=yb)     # warm (gate build, graph)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        net.stream_dev(xb[..., HOP * 10:], eb, chunks_per_call=1, state=stb, n_calls=nsteps - 10, out=yb[..., HOP * 10:])
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        best = ms if best is None else min(best, ms)
+    gb = stb.buf.numel() * stb.buf.element_size() / 1e9
+    return best, gb
+
+
+def measure_offline_bf16(net, dev, nb=256):
+    """BASELINE configs[2]: nb clips of 4 s in one forward(), bf16 tensor-core operands."""
+    g = torch.Generator().manual_seed(7000)
+    x = (0.1 * torch.randn(nb, 2, CLIP_SAMPLES, generator=g)).to(dev)
+    e = torch.rand(nb, 1, 256, generator=g).to(dev)
+    e = e / e.norm(dim=-1, keepdim=True)
+    net.set_option("bf16", 1)
+    try:
+        with torch.no_grad():
+            net(x[:32], e[:32])
+            torch.cuda.synchronize()
+            ms = _dev_time(lambda: net(x, e), 2, torch.cuda.synchronize)
+    finally:
+        net.set_option("bf16", 0)
+    return ms
+
+
+def measure_enrollment(dev, nb=1024, n=80000):
+    """BASELINE configs[3]: nb five-second utterances through EmbedTFGridNet.forward (device-resident input)."""
+    from lookoncetohear_b200 import EmbedTFGridNet
+    from lookoncetohear_b200.configs import EMBED_PARAMS
+    torch.manual_seed(0)
+    net = EmbedTFGridNet(**EMBED_PARAMS).eval().to(dev)
+    g = torch.Generator().manual_seed(8000)
+    x = (0.1 * torch.randn(64, 2, n, generator=g)).repeat(nb // 64, 1, 1)
+    x = (x * torch.linspace(0.5, 2.0, nb)[:, None, None]).to(dev)
+    with torch.no_grad():
+        net(x[:64])
+        torch.cuda.synchronize()
+        ms = _dev_time(lambda: net(x), 2, torch.cuda.synchronize)
+    del net
+    return ms
 
 
 def run_reference(args, rank, world):
@@ -281,12 +369,22 @@ def main():
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)          # the call ends with a stream sync; take the larger
     clocks = sampler.result()
 
-    tm = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    # ---- configs[4] per-GPU shape on EVERY rank: 256 streams per rank, one hop per step, max-over-ranks time ----
+    bs_ms, bs_gb, bs_err = 0.0, 0.0, None
+    NB_STREAMS, NB_STEPS = 256, 60
+    if not args.no_extras:
+        try:
+            bs_ms, bs_gb = measure_batched_streaming(net, dev, rank, NB_STREAMS, NB_STEPS)
+        except Exception as exc:                                   # never let a block break the bench line
+            bs_err = repr(exc)[:200]
+            bs_ms = float("inf")
+    barrier()
+    tm = torch.tensor([dev_ms, e2e_ms, bs_ms], device=dev, dtype=torch.float64)
     nl = torch.tensor([n_launched.value], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(nl, op=dist.ReduceOp.SUM)             # kernels of the whole job
-    dev_ms, e2e_ms = float(tm[0]), float(tm[1])
+    dev_ms, e2e_ms, bs_ms = float(tm[0]), float(tm[1]), float(tm[2])
     frames_total = world * FRAMES * args.steps
     value = frames_total / (dev_ms * 1e-3)
     e2e_value = frames_total / (e2e_ms * 1e-3)
@@ -343,37 +441,75 @@ def main():
                 torch.cuda.synchronize()
                 buf[str(c)] = FRAMES / (a.elapsed_time(b) * 1e-3)
         extras["frames_per_s_by_chunks_per_call"] = buf
-        # BASELINE configs[4] per-GPU shape: 256 independent streams advancing one hop per step.  This is
-        # the regime the HBM roofline of SURVEY.md 8(d) describes (5.5 MB of state per hop per stream).
+        # strictly causal streaming END TO END: per hop one H2D of the 8 ms chunk (+ look-ahead) from pinned memory,
+        # one predict() call, one D2H of the 128 output samples per ear -- what a live caller does
         try:
-            nb, nsteps = 256, 60
-            xb, _ = synth.mixture(nb, HOP * nsteps, seed0=5000)
-            xb = xb.to(dev)
-            eb = synth.embedding(nb, seed0=6000)[:, 0].to(dev)
-            yb = torch.empty(nb, 2, HOP * nsteps, device=dev)
-            best = None
-            for it in range(3):
-                stb = net.init_buffers(nb, dev)
-                net.stream_dev(xb, eb, chunks_per_call=1, state=stb, n_calls=10, out=yb)     # warm (gate build, graph)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                net.stream_dev(xb[..., HOP * 10:], eb, chunks_per_call=1, state=stb, n_calls=nsteps - 10,
-                               out=yb[..., HOP * 10:])
-                b.record()
-                torch.cuda.synchronize()
-                ms = a.elapsed_time(b)
-                best = ms if best is None else min(best, ms)
-            fps = nb * (nsteps - 10) / (best * 1e-3)
-            state_gb = stb.buf.numel() * stb.buf.element_size() / 1e9
-            pkb = peaks()
-            extras["batched_streaming_256"] = {
-                "streams": nb, "frames_per_s": fps, "rtf_aggregate": fps / 125.0, "ms_per_hop_step": best / (nsteps - 10),
-                "hbm_gbs_algorithmic": fps * BYTES_PER_FRAME / 1e9,
-                "hbm_frac": fps * BYTES_PER_FRAME / 1e9 / pkb["hbm_gbs"], "peak_source": pkb["source"],
-                "note": "state (%.2f GB) >> L2: every hop re-reads each stream's K/V rings from HBM" % state_gb}
-            del xb, yb, stb
-        except Exception as exc:                                   # never let an extra break the bench line
-            extras["batched_streaming_256"] = {"error": repr(exc)[:200]}
+            hops = 150
+            xin = torch.nn.functional.pad(x_cpu[..., :HOP * hops], (0, 64)).pin_memory()
+            yout = torch.empty(1, 2, HOP * hops).pin_memory()
+            xd = torch.empty(1, 2, HOP + 64, device=dev)
+            st = net.init_buffers(1, dev)
+            with torch.no_grad():
+                for i in range(hops):
+                    if i == 30:
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                    xd.copy_(xin[..., HOP * i:HOP * i + HOP + 64], non_blocking=True)
+                    yh, st = net.predict(xd, emb, st, pad=False)
+                    yout[..., HOP * i:HOP * (i + 1)].copy_(yh, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()           # the caller needs the samples before the next chunk exists
+            dt = time.perf_counter() - t0
+            extras["e2e_causal_frames_per_s"] = (hops - 30) / dt
+        except Exception as exc:
+            extras["e2e_causal_frames_per_s"] = {"error": repr(exc)[:200]}
+        extras["streaming_causal"] = {
+            "frames_per_s": extras.get("frames_per_s_unpipelined"), "rtf": (extras.get("frames_per_s_unpipelined") or 0) / 125.0,
+            "chunk_latency_device_us": extras.get("chunk_latency_device_us"), "chunk_latency_host_us": extras.get("chunk_latency_us"),
+            "e2e_frames_per_s": extras.get("e2e_causal_frames_per_s"),
+            "e2e_api": "per hop: pinned H2D of 192 samples x 2 mics, Net.predict(pad=False), D2H of 128 samples x 2 ears, stream sync",
+            "note": "hop t+1 is not started before hop t has finished: what a live 8 ms stream gets"}
+        pkb = peaks()
+        # ---- BASELINE configs[2]: offline batch of 256 x 4 s clips, bf16 tensor-core operands ----
+        try:
+            ms = measure_offline_bf16(net, dev, 256)
+            fps = 256 * FRAMES / (ms * 1e-3)
+            extras["offline_bf16_256"] = {
+                "clips": 256, "clip_s": FRAMES * 0.008, "ms": ms, "frames_per_s": fps, "rtf_aggregate": fps / 125.0,
+                "dtype": "bf16 weights on the tensor cores, activations as bf16 hi+lo (2 MMA passes), fp32 accumulate; fp32 recurrent "
+                         "state / LayerNorm / element-wise",
+                "tensor_tflops_algorithmic": fps * TC_FLOP_PER_FRAME / 1e12,
+                "tensor_frac": fps * TC_FLOP_PER_FRAME / 1e12 / pkb["bf16_tflops"], "tflops_total_algorithmic": fps * FLOP_PER_FRAME / 1e12,
+                "peak": pkb["bf16_tflops"], "peak_source": pkb["source"] + " bf16_tflops_sustained",
+                "note": "53 % of the FLOPs are tensor-core GEMMs (W_ih, Linears, Q|K|V); the recurrences (h W_hh), the 50-frame "
+                        "attention and the LayerNorms run on the CUDA cores"}
+        except Exception as exc:
+            extras["offline_bf16_256"] = {"error": repr(exc)[:200]}
+        # ---- BASELINE configs[3]: enrollment, 1024 utterances of 5 s ----
+        try:
+            ms = measure_enrollment(dev, 1024)
+            ups = 1024 / (ms * 1e-3)
+            extras["enrollment_1024"] = {
+                "utterances": 1024, "utt_s": 5.0, "ms": ms, "utt_per_s": ups, "tflops_algorithmic": ups * EMBED_FLOP_PER_UTT / 1e12,
+                "dtype": "fp32 in/out; tensor-core GEMMs as bf16x3 split products (3 MMA passes per product)",
+                "tensor_tflops_algorithmic": ups * EMBED_TC_FLOP_PER_UTT / 1e12,
+                "tensor_frac_algorithmic": ups * EMBED_TC_FLOP_PER_UTT / 1e12 / pkb["bf16_tflops"],
+                "tensor_frac_issued": 3 * ups * EMBED_TC_FLOP_PER_UTT / 1e12 / pkb["bf16_tflops"],
+                "peak": pkb["bf16_tflops"], "peak_source": pkb["source"] + " bf16_tflops_sustained"}
+        except Exception as exc:
+            extras["enrollment_1024"] = {"error": repr(exc)[:200]}
+    if rank == 0 and not args.no_extras:
+        pkb = peaks()
+        if bs_err is not None or bs_ms == float("inf"):
+            extras["batched_streaming"] = {"error": bs_err or "a rank failed"}
+        else:
+            fps = world * NB_STREAMS * (NB_STEPS - 10) / (bs_ms * 1e-3)
+            extras["batched_streaming"] = {
+                "streams_per_gpu": NB_STREAMS, "streams_total": world * NB_STREAMS, "frames_per_s": fps, "rtf_aggregate": fps / 125.0,
+                "ms_per_hop_step": bs_ms / (NB_STEPS - 10), "hbm_gbs_algorithmic_per_gpu": fps / world * BYTES_PER_FRAME / 1e9,
+                "hbm_frac": fps / world * BYTES_PER_FRAME / 1e9 / pkb["hbm_gbs"], "peak_source": pkb["source"],
+                "timing": "max over ranks of the device time of 50 hop-steps (best of 3), every rank its own 256 streams",
+                "note": "state (%.2f GB per GPU) >> L2: every hop re-reads each stream's K/V rings from HBM; "
+                        "algorithmic bytes 5.50 MB per hop per stream (SURVEY.md 8d)" % bs_gb}
     if rank == 0:
         # per-kernel device times of one streaming chain (CUDA events on the launching stream)
         prof = profile_chain(net, x_dev, emb, dev, cpc)

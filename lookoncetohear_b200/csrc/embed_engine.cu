@@ -519,7 +519,8 @@ int l2h_embed_set_option(void* handle, const char* name, int32_t value) {
     EmbedEngine* e = static_cast<EmbedEngine*>(handle);
     if (!e || !name) return fail(1, "bad argument");
     const std::string n(name);
-    if (n == "bf16") e->passes = value ? 1 : 3;      // 1: plain bf16 tensor-core operands; 0 (default): bf16x3 split, fp32-grade
+    if (n == "bf16") e->passes = value == 0 ? 3 : (value == 2 ? 1 : 2);   // 0 (default): bf16x3 split, fp32-grade; 1: bf16 weights x
+                                                                          // split activations; 2: plain bf16 operands
     else return fail(2, "unknown option: " + n);
     return 0;
 }

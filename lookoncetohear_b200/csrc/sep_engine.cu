@@ -56,11 +56,14 @@ struct SepEngine {
     // tensor-core path: bf16 hi/lo planes [2][N][K] of the GEMM weights, built on the device at commit
     struct PlaneSrc { int64_t wt_off; int K, N, ld, col0; int64_t plane_off; };
     std::vector<PlaneSrc> plane_srcs;
-    std::vector<int64_t> plane_of;      // per block: plane offsets of wih1, wl1, wih2, wl2, wqkv, [wih2|whh2]
+    std::vector<int64_t> plane_of;      // per block: plane offsets of wih1, wl1, wih2, wl2, wqkv, [wih2|whh2], wp
+    std::vector<int64_t> plane_stash;
     __nv_bfloat16* planes = nullptr;
     int64_t planes_total = 0;
+    bool cur_pdl = false;               // PDL attribute for the tensor-core launches of the chain being enqueued
     bool use_tc = true;                 // rows > TC_MIN_ROWS: dense contractions on tcgen05 (option "tensor_cores")
-    int tc_passes = 3;                  // 3 = bf16x3 split products (fp32 configs); 1 = plain bf16 operands (option "bf16")
+    int tc_passes = 3;                  // 3 = bf16x3 split products (fp32 configs); 2 = bf16 weights x split activations (option
+                                        // "bf16" = 1: the offline bf16 configuration); 1 = plain bf16 operands ("bf16" = 2)
     int64_t total = 0;
     std::map<std::string, Slot> slots;
     SepWeights w;
@@ -227,7 +230,7 @@ static void build_layout(SepEngine* e) {
             reg(wih1, 64, 512, 64, 0, p_ih1); reg(wl1, 128, 64, 128, 0, p_l1); reg(wih2, 64, 256, 64, 0, p_ih2);
             reg(wl2, 64, 64, 64, 0, p_l2); reg(wqkv, 64, NQKV, 64, 0, p_qkv);
             reg(wih2, 64, 256, 128, 0, p_cat); reg(whh2t, 64, 256, 128, 64, p_cat);      // [W_ih | W_hh]: k = [x | h]
-            for (int64_t v : {p_ih1, p_l1, p_ih2, p_l2, p_qkv, p_cat}) e->plane_of.push_back(v);
+            e->plane_stash = {p_ih1, p_l1, p_ih2, p_l2, p_qkv, p_cat};
         }
         bind(&W.lnq_g, plain(B + "attn_conv_Q.3.norm.weight", QK_DIM));
         bind(&W.lnq_b, plain(B + "attn_conv_Q.3.norm.bias", QK_DIM));
@@ -235,7 +238,15 @@ static void build_layout(SepEngine* e) {
         bind(&W.lnk_b, plain(B + "attn_conv_K.3.norm.bias", QK_DIM));
         bind(&W.lnv_g, plain(B + "attn_conv_V.3.norm.weight", V_DIM));
         bind(&W.lnv_b, plain(B + "attn_conv_V.3.norm.bias", V_DIM));
-        bind(&W.wp_t, transposed(B + "attn_concat_proj.0.weight", 64, 64, 64));
+        const int64_t wp = transposed(B + "attn_concat_proj.0.weight", 64, 64, 64);
+        bind(&W.wp_t, wp);
+        {
+            const int64_t p_p = e->planes_total;
+            e->planes_total += 64 * 64;
+            e->plane_srcs.push_back({wp, 64, 64, 64, 0, p_p});
+            for (int64_t v : e->plane_stash) e->plane_of.push_back(v);
+            e->plane_of.push_back(p_p);
+        }
         bind(&W.bp, plain(B + "attn_concat_proj.0.bias", 64));
         S[B + "attn_concat_proj.1.weight"] = Slot{slopes, 1, [slopes](const float* s, float* d) { d[slopes + 3] = s[0]; }};
         bind(&W.lnp_g, plain(B + "attn_concat_proj.3.norm.weight", FC));
@@ -329,7 +340,7 @@ static int set_attrs() {
 
 // ---- dense contractions on the tensor cores (csrc/umma_gemm.cuh) for calls with many rows --------------------------
 constexpr int64_t TC_MIN_ROWS = 2048;      // below this the 16-row CUDA-core tiles win (one streaming frame = 97 rows)
-enum { PL_IH1 = 0, PL_L1, PL_IH2, PL_L2, PL_QKV, PL_CAT, PL_PER_BLOCK };
+enum { PL_IH1 = 0, PL_L1, PL_IH2, PL_L2, PL_QKV, PL_CAT, PL_P, PL_PER_BLOCK };
 
 static umma::BPlanes tc_planes(const SepEngine* e, int blk, int which, int ld) {
     umma::BPlanes b;
@@ -340,14 +351,16 @@ static umma::BPlanes tc_planes(const SepEngine* e, int blk, int which, int ld) {
 
 // C[rows][N] = epi(LN?(A[rows][lda, first K]) W^T + bias) (+ R), plain row-major rows
 static int tc_rows_gemm(SepEngine* e, int blk, int which, const float* A, int64_t lda, int K, int N, const float* ln_g, const float* ln_b,
-                        const float* bias, const float* prelu_vec, const float* R, float* C, int64_t ldc, int64_t rows, cudaStream_t st) {
+                        const float* bias, const float* prelu_vec, const float* R, float* C, int64_t ldc, int64_t rows, cudaStream_t st,
+                        const float* prelu_scalar = nullptr) {
     umma::GemmDesc g;
     g.a0.base = A; g.a0.channels = K; g.a0.n_pos = rows; g.a0.pos_stride = lda;
     umma::set_plain_chunks(g, K, ln_g != nullptr);
     g.ln_g = ln_g; g.ln_b = ln_b;
     g.rows_per_seq = (int)rows; g.nseq = 1;
     g.b = tc_planes(e, blk, which, K); g.N = N; g.K = K; g.passes = e->tc_passes;
-    g.bias = bias; g.prelu_vec = prelu_vec; g.R = R; g.C = C; g.ldc = ldc;
+    g.bias = bias; g.prelu_vec = prelu_vec; g.prelu = prelu_scalar; g.R = R; g.C = C; g.ldc = ldc;
+    g.pdl = e->cur_pdl;
     std::string why;
     const cudaError_t ce = umma::launch(g, st, &why);
     if (ce != cudaSuccess) return fail(3, std::string("umma_gemm: ") + cudaGetErrorString(ce) + " " + why);
@@ -408,6 +421,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     };
     float* sbase = state + sizeof(StateHeader) / 4;
     const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS);
+    // measured (profiles/r02e): PDL on the tensor-core launches is slower (256 streams: 0.93 vs 0.87 ms per hop-step) -- a
+    // dependent CTA cannot become resident beside its predecessor (each holds ~200 KB of shared memory), so nothing overlaps
+    e->cur_pdl = false;
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
     CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
@@ -450,11 +466,12 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                 q.rows_per_seq = NF; q.nseq = B;
                 q.b = tc_planes(e, b, PL_CAT, 128); q.N = 256; q.K = 128; q.passes = e->tc_passes;
                 q.bias = W.b2; q.C = GX; q.ldc = 256; q.c_seq_stride = (int64_t)NF * 256;
+                q.pdl = false;
                 std::string why;
                 const cudaError_t ce = umma::launch(q, st, &why);
                 if (ce != cudaSuccess) return fail(3, std::string("umma_gemm (inter step): ") + cudaGetErrorString(ce) + " " + why);
             }
-            CK(launch_k(false, lstm_cell_rows_kernel, dim3((unsigned)((rows * 64 + 255) / 256)), dim3(256), 0, st, (const float*)GX, state, ss, b, Y, (int)rows));
+            CK(launch_k(pdl, lstm_cell_rows_kernel, dim3((unsigned)((rows * 64 + 255) / 256)), dim3(256), 0, st, (const float*)GX, state, ss, b, Y, (int)rows));
             if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
             if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
             MARK("mid");
@@ -539,8 +556,14 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                         (const float*)VALL, (const float*)state, ss, b, Z, T, 0));
         }
         MARK("attn");
-        CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
-                    (b == 0 && e->n_blocks > 1) ? 1 : 0, T));
+        if (tc) {      // Linear(64->64) + PReLU of all rows on the tensor cores, then LayerNorm(6208) + residual (+ gate) per frame
+            if (int rc = tc_rows_gemm(e, b, PL_P, Z, 64, 64, 64, nullptr, nullptr, W.bp, nullptr, nullptr, Y, 64, rows, st, W.slopes + 3)) return rc;
+            CK(launch_k(pdl, ln_frame_res_kernel, dim3(T, B), dim3(256), 0, st, (const float*)Y, X, (const float*)state, ss, W,
+                        (b == 0 && e->n_blocks > 1) ? 1 : 0, T));
+        } else {
+            CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
+                        (b == 0 && e->n_blocks > 1) ? 1 : 0, T));
+        }
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
@@ -1008,7 +1031,10 @@ int l2h_sep_commit_weights(void* handle, void* stream) {
                               e->planes + e->planes_total + ps.plane_off + ps.col0, st));
     CK(cudaStreamSynchronize(st));
     e->committed = true;
-    ++e->weight_gen;
+    e->w.gen = (int)(++e->weight_gen & 0x7fffff) + 1;      // never 0 (= a freshly initialised state)
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs carry the old generation in their kernel arguments
+    e->graphs.clear();
+    e->graph_kernels.clear();
     return 0;
 }
 
@@ -1127,6 +1153,13 @@ int l2h_sep_forward(void* handle, const float* x, int64_t xbs, int64_t xcs, int3
     return run_chain(e, a, static_cast<cudaStream_t>(stream), (flags & L2H_FLAG_GRAPH) != 0);
 }
 
+// One-hop calls are pipelined over hops (wavefront graph) only for FEW streams: with many streams every kernel of a hop
+// already fills the GPU, the dense stages run on the tensor cores (enqueue_chain) and the hops replay one chain graph.
+static bool pipeline_applies(const SepEngine* e, int batch, int cpc, int n_calls) {
+    if (!(cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1)) return false;
+    return !(e->use_tc && (int64_t)batch * NF > TC_MIN_ROWS);
+}
+
 int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const float* emb, void* state,
                         float* y_host, int32_t y_len, int32_t batch, int32_t n_calls, int32_t cpc,
                         float* x_stage, float* y_stage, void* ws, size_t ws_bytes, void* stream) {
@@ -1136,7 +1169,7 @@ int l2h_sep_stream_host(void* handle, const float* x_host, int32_t x_len, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // hops moved per host<->device round: one call's worth, or (one-hop calls, pipelining on) a group of up to
     // PIPE_MAX_FRAMES hops that then run as ONE wavefront-pipelined graph of one-hop chains
-    const bool pipe = cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1;
+    const bool pipe = pipeline_applies(e, batch, cpc, n_calls);
     int group = cpc;
     if (pipe) {
         const int64_t slot = pipe_slot_floats(e, batch);
@@ -1179,7 +1212,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
     e->launch_count += 1;
     ChainArgs a{x_dev, (int64_t)NMIC * x_len, x_len, x_len, emb, static_cast<float*>(state), y_dev,
                 (int64_t)NSRC * y_len, y_len, y_len, batch, cpc, static_cast<float*>(ws), ws_bytes, 0, 1};
-    if (cpc == 1 && e->use_pipe && e->use_mid && e->n_blocks == 3 && n_calls > 1) {
+    if (pipeline_applies(e, batch, cpc, n_calls)) {
         // groups of up to PIPE_MAX_FRAMES one-frame calls, each group one wavefront-pipelined graph
         const int64_t slot = pipe_slot_floats(e, batch);
         int kmax = (int)std::min<int64_t>(pipe_frames_for(e, batch), (int64_t)(ws_bytes / sizeof(float)) / slot);
@@ -1202,7 +1235,7 @@ int l2h_sep_stream_dev(void* handle, const float* x_dev, int32_t x_len, const fl
 int l2h_sep_stream_workspace_bytes(void* handle, int32_t batch, int32_t chunks_per_call, size_t* bytes) {
     SepEngine* e = static_cast<SepEngine*>(handle);
     if (!e || !bytes || batch <= 0 || chunks_per_call <= 0) return fail(1, "bad argument");
-    if (chunks_per_call == 1 && e->use_pipe)
+    if (pipeline_applies(e, batch, chunks_per_call, 2))
         *bytes = (size_t)pipe_slot_floats(e, batch) * pipe_frames_for(e, batch) * sizeof(float);
     else
         *bytes = (size_t)carve(e->n_blocks, batch, chunks_per_call, 0).total * sizeof(float);
@@ -1237,7 +1270,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else if (n == "tensor_cores") e->use_tc = value != 0;
-    else if (n == "bf16") e->tc_passes = value ? 1 : 3;
+    else if (n == "bf16") e->tc_passes = value == 0 ? 3 : (value == 2 ? 1 : 2);   // 1: bf16 weights x split activations; 2: plain bf16 both
     else if (n == "graph_stats") e->graph_stats = value != 0;
     else return fail(2, "unknown option: " + n);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);     // cached graphs were built with the old setting

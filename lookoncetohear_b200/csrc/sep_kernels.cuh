@@ -20,6 +20,7 @@ struct SepWeights {           // device pointers into the packed weight buffer
     const float* lne_b;
     const float* wd;          // [64][4][9]   deconv (c, o, i*3+j)
     const float* bd;          // [4]
+    int gen;                  // weight generation (bumped by every commit): part of the speaker-gate memo key
 };
 
 struct BlockWeights {
@@ -195,7 +196,8 @@ __device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ 
     const int tid = threadIdx.x;
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float e = emb[(int64_t)b * SPK + tid];
-    const int same = __syncthreads_and(e == st[ST_EMB + tid]);
+    // memo key: the embedding AND the weight generation (a reused state must not keep a gate built from old weights)
+    const int same = __syncthreads_and(e == st[ST_EMB + tid] && __float_as_int(st[ST_GEN]) == w.gen);
     if (same) return;
     float* es = red + 32;                      // [256] embedding
     es[tid] = e;
@@ -232,6 +234,7 @@ __device__ void spk_gate_cta(const float* __restrict__ emb, float* __restrict__ 
         st[ST_GATE + f * CH + c] = (p[i] - mu) * rs * __ldg(w.lne_g + i) + __ldg(w.lne_b + i);
     }
     st[ST_EMB + tid] = e;
+    if (tid == 0) st[ST_GEN] = __int_as_float(w.gen);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1008,6 +1011,46 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tail of the attention output for calls with many rows, where the Linear(64->64) + PReLU ran as a tensor-core GEMM
+// into P: LayerNorm over the frame's (F, C) = 6208 values + residual (+ the speaker gate after block 0)
+// (tfgridnet_causal.py:583-588, :250-251).  Same arithmetic as the tail of attn_out_kernel.  grid (T, B), 256 threads.
+__global__ void __launch_bounds__(256)
+ln_frame_res_kernel(const float* __restrict__ P, float* __restrict__ X, const float* __restrict__ state, int64_t sstride,
+                    BlockWeights w, int apply_gate, int T) {
+    __shared__ float red[32];
+    __shared__ __align__(16) float Ps[FC];
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    griddep_launch();
+    griddep_wait();
+    const int64_t off = ((int64_t)b * T + t) * FC;
+    float s = 0.f;
+    for (int i = tid; i < FC / 4; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(P + off)[i];
+        reinterpret_cast<float4*>(Ps)[i] = v;
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mu = block_sum(s, red) * (1.f / FC);
+    float q = 0.f;
+    for (int i = tid; i < FC; i += 256) { const float d = Ps[i] - mu; q += d * d; }
+    const float rs = rsqrtf(block_sum(q, red) * (1.f / FC) + 1e-5f);
+    const float* gate = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_GATE;
+    float* xr = X + off;
+    for (int i = tid; i < FC / 4; i += 256) {
+        float4 x4 = reinterpret_cast<const float4*>(xr)[i];
+        const float4 p4 = reinterpret_cast<const float4*>(Ps)[i];
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.lnp_g) + i);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.lnp_b) + i);
+        x4.x += (p4.x - mu) * rs * g4.x + b4.x; x4.y += (p4.y - mu) * rs * g4.y + b4.y;
+        x4.z += (p4.z - mu) * rs * g4.z + b4.z; x4.w += (p4.w - mu) * rs * g4.w + b4.w;
+        if (apply_gate) {
+            const float4 gt = reinterpret_cast<const float4*>(gate)[i];
+            x4.x *= gt.x; x4.y *= gt.y; x4.z *= gt.z; x4.w *= gt.w;
+        }
+        reinterpret_cast<float4*>(xr)[i] = x4;
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // One inter-LSTM step for many streams, cell part only (tfgridnet_causal.py:524-532 with T = 1): the gate

@@ -46,12 +46,13 @@ static_assert(sizeof(StateHeader) == 64, "header");
 
 // per-stream record, offsets in floats
 constexpr int64_t ST_EMB = 0;                                   // [256] embedding the gate was built from
-constexpr int64_t ST_GATE = ST_EMB + SPK;                       // [97][64]  LN(W e + b), (f, c) order
+constexpr int64_t ST_GEN = ST_EMB + SPK;                        // [4] slot 0: weight generation (int bits) the gate was built with
+constexpr int64_t ST_GATE = ST_GEN + 4;                         // [97][64]  LN(W e + b), (f, c) order
 constexpr int64_t ST_CONV = ST_GATE + FC;                       // [2 parity][2 frames][4][97]
 constexpr int64_t ST_DECONV = ST_CONV + 2 * 2 * 4 * NF;         // [2][2][97][64]
 constexpr int64_t ST_ISTFT = ST_DECONV + 2 * 2 * FC;            // [2][2 ears][194]
 constexpr int64_t ST_BLK = ST_ISTFT + 2 * NSRC * NROW;          // blocks start
-constexpr int64_t BK_K = 0;                                     // ring [4][52][584], slot = frame mod 52
+constexpr int64_t BK_K = 0;                                     // ring [4][RING][584], slot = frame mod RING
 constexpr int64_t BK_V = BK_K + (int64_t)NHEAD * RING * QK_LD;  // ring [4][RING][1552]
 constexpr int64_t BK_H = BK_V + (int64_t)NHEAD * RING * V_DIM;  // [97][64]
 constexpr int64_t BK_C = BK_H + FC;                             // [97][64]

@@ -76,8 +76,8 @@ struct Plan { int BN, resident, nstg, nop; size_t smem; bool ok; };
 // A operand slots (small K), else A and B stream through a ring of operand slots together
 inline Plan plan_for(const GemmDesc& g, int BN) {
     Plan pl{BN, 0, 2, 0, 0, false};
-    const int planes = g.passes > 1 ? 2 : 1;
-    const size_t opA = (size_t)planes * OPA_PLANE;
+    const int planes_a = g.passes > 1 ? 2 : 1, planes = g.passes > 2 ? 2 : 1;
+    const size_t opA = (size_t)planes_a * OPA_PLANE;
     const size_t opB = (size_t)planes * (g.b.mn_major ? (size_t)((BN + 63) / 64) * 8192 : (size_t)BN * 128);
     const size_t fixed = 1024 + EPI_BYTES;
     if (!g.b_by_seq && fixed + 2 * STG_BYTES + 2 * opA + (size_t)g.n_chunks * opB <= SMEM_LIMIT) {
@@ -101,7 +101,7 @@ cudaError_t launch(const GemmDesc& g, cudaStream_t st, std::string* why) {
     auto bad = [&](const char* m) { if (why) *why = m; return cudaErrorInvalidValue; };
     if (g.n_chunks <= 0 || g.n_chunks > MAX_CHUNKS) return bad("k-chunk count");
     if (g.N <= 0 || g.rows_per_seq <= 0 || g.nseq <= 0) return bad("empty problem");
-    if (g.passes != 1 && g.passes != 3) return bad("passes must be 1 or 3");
+    if (g.passes < 1 || g.passes > 3) return bad("passes must be 1, 2 or 3");
     cudaError_t e = configure();
     if (e != cudaSuccess) return e;
     Params p;
@@ -131,7 +131,7 @@ cudaError_t launch(const GemmDesc& g, cudaStream_t st, std::string* why) {
     p.idesc = make_idesc_bf16(p.BN, p.b_mn_major);
     p.b_resident = pl.resident; p.nstg = pl.nstg; p.nop = pl.nop;
     const size_t smem = pl.smem;
-    const int planes = g.passes > 1 ? 2 : 1;
+    const int planes = g.passes > 2 ? 2 : 1;      // B planes the tensor map exposes
     int cols = 32;
     while (cols < 2 * p.BN) cols <<= 1;
     p.tmem_cols = cols;
@@ -177,8 +177,14 @@ cudaError_t launch(const GemmDesc& g, cudaStream_t st, std::string* why) {
     groups = (m_tiles + per - 1) / per;
     const int grid = (int)groups * p.n_tiles_n;
     ++g_launches;
-    umma_gemm_kernel<<<grid, NTHREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, umma_gemm_kernel, p);
 }
 
 // ---- B operand preparation: fp32 matrix (any strides) -> bf16 hi/lo planes [2][rows][cols] ---------------------

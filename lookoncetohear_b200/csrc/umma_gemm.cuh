@@ -11,8 +11,8 @@
 //     -- nn.LayerNorm semantics -- so that LN -> Linear pairs are one kernel);
 //   * ONE thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M = 128, N = BN <= 256) with the accumulator in
 //     TENSOR MEMORY.  passes = 3 gives fp32-grade products from three bf16 MMAs
-//     (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, relative error ~2^-16 per product: the "bf16x3" split), passes = 1 is plain
-//     bf16 (the offline bf16 configuration);
+//     (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, relative error ~2^-16 per product: the "bf16x3" split); passes = 2 drops the
+//     b_lo term (bf16 weights, activations still split: the offline bf16 configuration); passes = 1 is plain bf16;
 //   * the epilogue warpgroup reads the accumulator back with tcgen05.ld (thread = row = TMEM lane), applies
 //     bias / PReLU / residual / scale and stores fp32 rows; accumulators are double-buffered in TMEM so the epilogue
 //     of tile i overlaps the MMAs of tile i+1.

@@ -50,6 +50,7 @@ struct GemmDesc {
     const float* ln_g = nullptr;
     const float* ln_b = nullptr;
     float alpha = 1.f;
+    bool pdl = false;                 // launch with the programmatic-serialization attribute (kernel chains)
 };
 
 inline void set_plain_chunks(GemmDesc& g, int K, bool ln = false) {

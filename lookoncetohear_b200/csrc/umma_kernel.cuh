@@ -91,10 +91,15 @@ umma_gemm_kernel(const __grid_constant__ Params p) {
     __shared__ float ln_s[128];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // programmatic dependent launch: the successor may become resident now; THIS kernel's barrier / TMEM set-up and its
+    // weight-slab loads run under the predecessor's tail, and only the roles that touch chain data (the TMA producer
+    // before the first activation tile, the epilogue before residual reads / stores) wait for the predecessor
+    griddep_launch();
     const unsigned smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
     const int passes = p.passes, BN = p.BN, nop = p.nop, NSTG = p.nstg;
-    const int planes = passes > 1 ? 2 : 1;
-    const unsigned opA_bytes = (unsigned)planes * OPA_PLANE;
+    const int planes_a = passes > 1 ? 2 : 1;          // passes: 1 = a_hi b_hi; 2 = + a_lo b_hi (bf16 weights, split activations);
+    const int planes = passes > 2 ? 2 : 1;            //         3 = + a_hi b_lo (bf16x3: fp32-grade products).  `planes` = B planes
+    const unsigned opA_bytes = (unsigned)planes_a * OPA_PLANE;
     const int nb64 = (BN + 63) >> 6;
     const unsigned opB_plane = p.b_mn_major ? (unsigned)nb64 * 8192u : (unsigned)BN * 128u;
     const unsigned opB_bytes = (unsigned)planes * opB_plane;
@@ -145,6 +150,7 @@ umma_gemm_kernel(const __grid_constant__ Params p) {
                 mbar_expect_tx(&bar_b_full, opB_bytes * (unsigned)p.n_chunks);
                 for (int j = 0; j < p.n_chunks; ++j) load_b(opB0 + j * opB_bytes, &bar_b_full, j, 0);
             }
+            griddep_wait();                           // activations (and a batched B) come from the predecessor
             unsigned it = 0;
             for (int mt = gi; mt < m_tiles; mt += groups) {
                 const int p0 = (mt % p_tiles) * p.P_TILE, seq0 = (mt / p_tiles) * p.S_TILE;
@@ -268,8 +274,10 @@ umma_gemm_kernel(const __grid_constant__ Params p) {
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
         const unsigned tb = epi0 + (unsigned)q * 4096u;
-        const float slope = p.prelu ? __ldg(p.prelu) : 0.f;
+        const float slope1 = p.prelu ? __ldg(p.prelu) : 1.f;      // scalar PReLU slope (1 = identity)
+        const bool has_prelu = p.prelu != nullptr || p.prelu_vec != nullptr;
         const int chunk = lane & 7, rsub = lane >> 3;
+        griddep_wait();                               // C may still be read, R still be written by the predecessor
         unsigned tl = 0;
         for (int mt = gi; mt < m_tiles; mt += groups, ++tl) {
             const int p0 = (mt % p_tiles) * p.P_TILE, seq0 = (mt / p_tiles) * p.S_TILE;
@@ -286,6 +294,16 @@ umma_gemm_kernel(const __grid_constant__ Params p) {
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + a * (unsigned)BN;
             for (int cb = 0; cb < BN; cb += 32) {
                 float v[32];
+                const int nl = cb + chunk * 4;         // this lane's four columns inside the tile (after the transpose)
+                const int n = n0 + nl;
+                const bool col_ok = nl < BN && n < p.N;
+                const bool full4 = col_ok && (n + 3 < p.N) && p.vec_ok;
+                // per-column epilogue operands of this lane (L1 hits after the first tile: same columns every tile)
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(slope1, slope1, slope1, slope1);
+                if (full4) {
+                    if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (p.prelu_vec) s4 = __ldg(reinterpret_cast<const float4*>(p.prelu_vec + n));
+                }
                 __syncwarp();                          // tcgen05.ld is warp-collective; also: transpose buffer free again
                 tc_ld16(taddr + cb, v);
                 if (cb + 16 < BN) tc_ld16(taddr + cb + 16, v + 16);
@@ -300,40 +318,55 @@ umma_gemm_kernel(const __grid_constant__ Params p) {
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tb + (unsigned)lane * 128u + ((c ^ (unsigned)(lane & 7)) << 4)),
                                  "f"(v[c * 4]), "f"(v[c * 4 + 1]), "f"(v[c * 4 + 2]), "f"(v[c * 4 + 3]) : "memory");
                 __syncwarp();
-                const int nl = cb + chunk * 4;         // this lane's four columns inside the tile
-                const int n = n0 + nl;
-                const bool col_ok = nl < BN && n < p.N;
-                const bool full4 = col_ok && (n + 3 < p.N) && p.vec_ok;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (full4) {
-                    if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    if (p.prelu_vec) s4 = __ldg(reinterpret_cast<const float4*>(p.prelu_vec + n));
-                }
+                if (__all_sync(0xffffffffu, full4 || !col_ok)) {
+                    // ---- fast path: whole float4 groups.  Row offsets first (and the residual loads in flight), then math
+                    long long co[8];
+                    unsigned okm = 0;
 #pragma unroll
-                for (int itr = 0; itr < 8; ++itr) {
-                    const int row = itr * 4 + rsub;
-                    float4 o;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                                 : "r"(tb + (unsigned)row * 128u + (((unsigned)chunk ^ (unsigned)(row & 7)) << 4)));
-                    const long long co = __shfl_sync(0xffffffffu, coff, row);
-                    const int ok = __shfl_sync(0xffffffffu, valid, row);
-                    if (!ok || !col_ok) continue;
-                    o.x *= p.alpha; o.y *= p.alpha; o.z *= p.alpha; o.w *= p.alpha;
-                    if (full4) {
-                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                        if (p.prelu) { o.x = prelu(o.x, slope); o.y = prelu(o.y, slope); o.z = prelu(o.z, slope); o.w = prelu(o.w, slope); }
-                        if (p.prelu_vec) { o.x = prelu(o.x, s4.x); o.y = prelu(o.y, s4.y); o.z = prelu(o.z, s4.z); o.w = prelu(o.w, s4.w); }
-                        if (p.R) { const float4 rr = *reinterpret_cast<const float4*>(p.R + co + n); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                        *reinterpret_cast<float4*>(p.C + co + n) = o;
-                    } else {
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int row = itr * 4 + rsub;
+                        co[itr] = __shfl_sync(0xffffffffu, coff, row) + n;
+                        okm |= (unsigned)(__shfl_sync(0xffffffffu, valid, row) & (col_ok ? 1 : 0)) << itr;
+                    }
+                    float4 rr[8];
+                    if (p.R) {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            rr[itr] = ((okm >> itr) & 1u) ? *reinterpret_cast<const float4*>(p.R + co[itr]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int row = itr * 4 + rsub;
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                     : "r"(tb + (unsigned)row * 128u + (((unsigned)chunk ^ (unsigned)(row & 7)) << 4)));
+                        o.x = fmaf(o.x, p.alpha, b4.x); o.y = fmaf(o.y, p.alpha, b4.y); o.z = fmaf(o.z, p.alpha, b4.z); o.w = fmaf(o.w, p.alpha, b4.w);
+                        if (has_prelu) {               // max(x,0) + slope * min(x,0)
+                            o.x = fmaf(s4.x, fminf(o.x, 0.f), fmaxf(o.x, 0.f)); o.y = fmaf(s4.y, fminf(o.y, 0.f), fmaxf(o.y, 0.f));
+                            o.z = fmaf(s4.z, fminf(o.z, 0.f), fmaxf(o.z, 0.f)); o.w = fmaf(s4.w, fminf(o.w, 0.f), fmaxf(o.w, 0.f));
+                        }
+                        if (p.R) { o.x += rr[itr].x; o.y += rr[itr].y; o.z += rr[itr].z; o.w += rr[itr].w; }
+                        if ((okm >> itr) & 1u) *reinterpret_cast<float4*>(p.C + co[itr]) = o;
+                    }
+                } else {
+                    // ---- cold path: ragged N or unaligned rows, element by element
+#pragma unroll 1
+                    for (int itr = 0; itr < 8; ++itr) {
+                        const int row = itr * 4 + rsub;
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                     : "r"(tb + (unsigned)row * 128u + (((unsigned)chunk ^ (unsigned)(row & 7)) << 4)));
+                        const long long cor = __shfl_sync(0xffffffffu, coff, row);
+                        const int ok = __shfl_sync(0xffffffffu, valid, row);
+                        if (!ok || !col_ok) continue;
                         const float ov[4] = {o.x, o.y, o.z, o.w};
                         for (int e = 0; e < 4 && n + e < p.N; ++e) {
-                            float x = ov[e];
+                            float x = ov[e] * p.alpha;
                             if (p.bias) x += __ldg(p.bias + n + e);
-                            if (p.prelu) x = prelu(x, slope);
+                            if (p.prelu) x = prelu(x, slope1);
                             if (p.prelu_vec) x = prelu(x, __ldg(p.prelu_vec + n + e));
-                            if (p.R) x += p.R[co + n + e];
-                            p.C[co + n + e] = x;
+                            if (p.R) x += p.R[cor + n + e];
+                            p.C[cor + n + e] = x;
                         }
                     }
                 }

@@ -285,3 +285,54 @@ def test_launch_counter_counts_graph_nodes(model, dev):
     torch.cuda.synchronize()
     _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
     assert n.value == 8 * 23 + 3 * 2 + 1 + 1
+
+
+def test_fold_mid_c_option(model, dev):
+    """Engine option "fold_mid_c": the inter Linear runs inside the serial mid kernel and the Q/K/V projection inside
+    qkv_kernel (three kernels fewer per hop).  A different kernel split, so not bit-identical to the default -- the
+    gate is the usual 1e-3 against the oracle plus 1e-5 against the default path; pipelined == sequential bit for bit
+    holds within the option."""
+    net, sd = model
+    T, B = 70, 2
+    x, _ = synth.mixture(B, 128 * T, seed0=191)
+    e = synth.embedding(B, seed0=192)
+    xd, ed = x.to(dev), e[:, 0].to(dev)
+    y_def = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+    try:
+        net.set_option("fold_mid_c", 1)
+        y_pipe = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+        net.set_option("pipeline", 0)
+        y_seq = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+    finally:
+        net.set_option("pipeline", 1)
+        net.set_option("fold_mid_c", 0)
+    assert torch.equal(y_pipe, y_seq)
+    assert rs.rel_l2(y_pipe, y_def) < 1e-5
+    _check(y_pipe[:1], rs.sep_forward(sd, x[:1], e[:1]))
+
+
+def test_gate_memo_follows_weight_changes(tsh_params, dev):
+    """The speaker gate is memoised in the state (the reference recomputes it every call, tfgridnet_causal.py:247-248).
+    The memo key is (embedding, weight generation): after load_state_dict with a different embed_to_feats_proj a REUSED
+    state with the SAME embedding must produce the new weights' output."""
+    torch.manual_seed(21)
+    net = Net(**tsh_params).eval().to(dev)
+    x, _ = synth.mixture(1, 128 * 6, seed0=31)
+    e = synth.embedding(1, seed0=32)
+    xp = torch.nn.functional.pad(x, (0, 64)).to(dev)
+    st = net.init_buffers(1, dev)
+    with torch.no_grad():
+        net.predict(xp[..., :192], e[:, 0].to(dev), st, pad=False)                # builds the gate with the old weights
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        sd["tfgridnet.embed_to_feats_proj.0.weight"] = sd["tfgridnet.embed_to_feats_proj.0.weight"] * 1.7 + 0.01
+        net.load_state_dict(sd)
+        # same state object, same embedding, new weights: continue the stream ...
+        y1 = torch.cat([net.predict(xp[..., 128 * i:128 * i + 192], e[:, 0].to(dev), st, pad=False)[0] for i in range(1, 6)], -1).cpu()
+    # ... and compare with the oracle continuing from the state after hop 0 with the NEW weights
+    sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    torch.manual_seed(21)
+    sd_old = {k: v.detach().clone() for k, v in Net(**tsh_params).state_dict().items()}
+    st_ref = rs.sep_init_state(sd_old, 1)
+    rs.sep_predict(sd_old, xp[..., :192].cpu(), e[:, 0], st_ref, pad=False)
+    y_ref = torch.cat([rs.sep_predict(sd_cpu, xp[..., 128 * i:128 * i + 192].cpu(), e[:, 0], st_ref, pad=False)[0] for i in range(1, 6)], -1)
+    assert rs.rel_l2(y1, y_ref) <= 1e-3

@@ -8,7 +8,8 @@ from lookoncetohear_b200.configs import EMBED_PARAMS
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 net = EmbedTFGridNet(**EMBED_PARAMS).eval().to(dev)
-for B in (1, 8, 32):
+batches = [int(a) for a in sys.argv[1:]] or [1, 8, 32]
+for B in batches:
     x = synth.enrollment(B, 80000).to(dev)
     with torch.no_grad():
         net(x); torch.cuda.synchronize()

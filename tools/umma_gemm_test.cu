@@ -139,7 +139,7 @@ static int run_case(const Case& c, bool timing = false) {
         }
     }
     const double rel = std::sqrt(num / std::max(den, 1e-30));
-    const double tol = c.small_int ? 1e-6 : (c.passes == 3 ? 5e-5 : 2e-2);
+    const double tol = c.small_int ? 1e-6 : (c.passes == 3 ? 5e-5 : (c.passes == 2 ? 8e-3 : 2e-2));
     const bool ok = bad == 0 && rel <= tol;
     printf("[%s] rel-L2 %.3e  max-abs %.3e  non-finite %d  -> %s\n", c.name, rel, maxabs, bad, ok ? "OK" : "FAIL");
     cudaFree(dA); cudaFree(dA1); cudaFree(dW); cudaFree(dbias); cudaFree(dsl); cudaFree(dg); cudaFree(dbt); cudaFree(dR); cudaFree(dC); cudaFree(dB);
@@ -156,6 +156,8 @@ int main(int argc, char** argv) {
         {"exact_k64_n64_p3",            1,  1000,  64, 1, 1000, 0,   64, 3, false, false, false, false, true,  1.f, false, false, false, 0},
         {"rand_k64_n64_p3",             1,  1000,  64, 1, 1000, 0,   64, 3, false, false, false, false, false, 1.f, false, false, false, 0},
         {"rand_k64_n64_p1",             1,  1000,  64, 1, 1000, 0,   64, 1, false, false, false, false, false, 1.f, false, false, false, 0},
+        {"rand_k128_n256_p2",           1,  3000, 128, 1, 3000, 0,  256, 2, false, true,  false, true,  false, 1.f, false, false, false, 0},
+        {"win4_k256_n512_p2_stream",   37,    65,  64, 4,   62, 0,  512, 2, true,  true,  false, false, false, 1.f, false, false, false, 0},
         {"k256_n512_bias_prelu",        1,  3000, 256, 1, 3000, 0,  512, 3, false, true,  true,  false, false, 1.f, false, false, false, 0},
         {"ln_k64_n256_res",             1,  5000,  64, 1, 5000, 0,  256, 3, true,  true,  false, true,  false, 1.f, false, false, false, 0},
         {"ln_k64_n512",                 1,  2000,  64, 1, 2000, 0,  512, 3, true,  true,  false, false, false, 1.f, false, false, false, 0},
