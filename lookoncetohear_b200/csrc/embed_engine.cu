@@ -15,6 +15,7 @@
 #include "embed_kernels.cuh"
 #include "lstm.cuh"
 #include "umma_host.cuh"
+#include "tc_lstm.cuh"
 
 namespace l2h {
 
@@ -313,6 +314,7 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
                        " is current: commit the weights again there (EmbedTFGridNet.to(device) does)");
     if (e->attrs_dev != cur_dev) {
         CK(configure_lstm());
+        CK(configure_tc_lstm());
         CK(umma::configure());
         CK(cudaFuncSetAttribute(eattn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EAOUT_SMEM));
         e->attrs_dev = cur_dev;
@@ -365,7 +367,8 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
             l.gx = GX; l.gx_ld = 512; l.out = HC; l.out_ld = 128; l.whh = inter ? W.whh2 : W.whh1;
             l.nseq = nseq; l.L = steps; l.inner_count = 1; l.outer_stride = steps; l.inner_stride = 0; l.step_stride = 1;
             l.ndir = 2;
-            CK(launch_lstm_rec(l, st));
+            if ((int64_t)l.nseq * l.ndir >= 2048) CK(launch_tc_lstm(l, passes, st));      // many sequences: recurrence on the tensor cores
+            else CK(launch_lstm_rec(l, st));
             // ---- ConvTranspose1d(128->64, k=4) + residual: output position p reads h rows p-3 .. p; rows outside the
             // sequence are the zero-filled halo of the tensor map ----------------------------------------------------
             umma::GemmDesc c;

@@ -17,6 +17,7 @@
 #include "../../include/lookonce_b200.h"
 #include "gemm.cuh"
 #include "umma_host.cuh"
+#include "tc_lstm.cuh"
 #include "lstm.cuh"
 #include "sep_kernels.cuh"
 #include "mid_kernel.cuh"
@@ -333,6 +334,7 @@ static int set_attrs() {
     CK(configure_rows_gemm());
     CK(configure_lstm());
     CK(umma::configure());
+    CK(configure_tc_lstm());
     g_attr_done[dev_ord] = true;
     return 0;
 }
@@ -347,6 +349,13 @@ static umma::BPlanes tc_planes(const SepEngine* e, int blk, int which, int ld) {
     b.base = e->planes + e->plane_of[(size_t)blk * PL_PER_BLOCK + which];
     b.ld = ld; b.plane_stride = e->planes_total; b.nz = 1;
     return b;
+}
+
+// the recurrence: tensor cores when there are enough sequences to fill the GPU with 32-sequence CTAs, else lstm.cuh
+constexpr int TCL_MIN_SEQDIRS = 2048;
+static cudaError_t lstm_any(SepEngine* e, const LstmArgs& l, cudaStream_t st, bool pdl) {
+    if (e->use_tc && (int64_t)l.nseq * l.ndir >= TCL_MIN_SEQDIRS) return launch_tc_lstm(l, e->tc_passes, st, pdl);
+    return launch_lstm_rec(l, st, pdl);
 }
 
 // C[rows][N] = epi(LN?(A[rows][lda, first K]) W^T + bias) (+ R), plain row-major rows
@@ -447,7 +456,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
         l.nseq = B * T; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1;
         l.ndir = 2;
-        CK(launch_lstm_rec(l, st, pdl));
+        CK(lstm_any(e, l, st, pdl));
         MARK("lstm_intra");
         if (tc_mid) {
             // many streams, one hop: the row-local middle of the block as four tensor-core GEMMs and the cell update.
@@ -519,7 +528,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             l.hc_outer_stride = ss;
             l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
             l.step_stride = NF; l.ndir = 1;
-            CK(launch_lstm_rec(l, st, pdl));
+            CK(lstm_any(e, l, st, pdl));
             MARK("lstm_inter");
             if (tc) {
                 if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
