@@ -526,6 +526,13 @@ def main():
                 "traffic": 11392.0 if dom[0] == "lstm_intra" else None, "peak_source": pk["source"],
                 "alg_bytes_per_launch": alg, "mean_us_per_launch": 1e3 * dom[1]["ms_mean"],
                 "share_of_chain": dom[1]["ms_total"] / sum(v["ms_total"] for v in prof.values()),
+                # the model that governs batch 1: the chain cannot be shorter than its 3 x 97 dependent recurrent steps.
+                # t_step_floor = 0.23 us: the FMA + shuffle + barrier floor of one 256x64 step on one SM
+                # (profiles/r01c_lstm_microbench.txt); fma_pipe_pct from the ncu capture profiles/r01e_lstm_rec3_full.md
+                "latency_model": {"serial_steps": 3 * 97, "t_step_floor_us": 0.23, "t_step_measured_us": 1e3 * dom[1]["ms_mean"] / 97.0,
+                                  "chain_us": 1e3 * sum(v["ms_total"] for v in prof.values()),
+                                  "latency_frac": 3 * 97 * 0.23 / (1e3 * sum(v["ms_total"] for v in prof.values())),
+                                  "fma_pipe_pct_of_dominant_kernel": 27.0},
                 "note": "batch-1 streaming is latency-bound (serial LSTM chain, 13 MB working set resident in L2); "
                         "whole-chain algorithmic rate: %.1f GB/s, %.2f TFLOP/s fp32" % (
                             value / world * BYTES_PER_FRAME / 1e9, value / world * FLOP_PER_FRAME / 1e12)}
