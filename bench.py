@@ -47,6 +47,11 @@ FLOP_PER_FRAME = 74.67e6
 BYTES_PER_FRAME = 5.50e6
 
 
+def workload_name():
+    return ("streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); %.1f s clip = %d hops per step, "
+            "fresh state per step" % (FRAMES * 0.008, FRAMES))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -250,8 +255,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf": value / 125.0,
-        "config": {"workload": "streaming separation, 8 ms chunks, batch=1, fp32 (BASELINE configs[1])",
-                   "chunks_per_call": args.chunks_per_call, "clip_s": 4.0, "sample": f"{sample_frames} hops per step"},
+        "config": {"workload": workload_name(), "chunks_per_call": args.chunks_per_call,
+                   "sample": f"bounded sample: {sample_frames} hops (1 s) of the same 4 s clip per step, strictly hop by hop on the CPU"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
                          "sample": f"{sample_frames} hops of the 4 s clip per step, chunked predict(pad=False), "
                                    f"{cpu_model_name()}"},
@@ -552,8 +557,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": value / world / 125.0,
-            "config": {"workload": "streaming separation, 8 ms chunks, batch=1 per GPU, fp32 (BASELINE configs[1]); "
-                                   "%.1f s clip = %d hops per step, fresh state per step" % (FRAMES * 0.008, FRAMES),
+            "config": {"workload": workload_name(),
                        "chunks_per_call": cpc,
                        "pipeline": "wavefront over (block, hop) stages: up to %d one-hop chains per multi-stream CUDA graph; every "
                                    "hop is its own T=1 kernel chain with the state carried hop to hop, results bit-identical to the "

@@ -217,6 +217,18 @@ int l2h_eval_metrics(const float* est_dev, const float* target_dev, const float*
                      int32_t n_samples, const float* emb_dev, const float* emb_gt_dev, int32_t emb_dim, float* out_dev,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Binaural rendering of mono events on the device (the data-side arithmetic of the reference's simulators):
+ *   events[b][s][ear] = convolve(src[b][s], rir[b][s][ear])[:n_samples]      src/datasets/multi_ch_simulator.py:56-58
+ *   noise scaled by noise_scale[b]; norm = max|sum(events) + noise|; if norm > 1 events and noise are divided by it;
+ *   mixture = sum(events) + noise                                   src/datasets/MixLibriSpeechNoisyEnrollNorm.py:179-202
+ * src_dev [batch][n_src][n_samples] mono; rir_dev [batch][n_src][2][rir_len] (already at the sampling rate of src);
+ * noise_dev [batch][2][n_samples] or NULL; noise_scale_dev [batch] or NULL (= 1); events_dev [batch][n_src][2][n_samples];
+ * mixture_dev [batch][2][n_samples]; norm_dev [batch] or NULL; scratch_dev: batch * 4 bytes.  Asynchronous on `stream`. */
+int l2h_render_binaural(const float* src_dev, const float* rir_dev, const float* noise_dev, const float* noise_scale_dev,
+                        int32_t batch, int32_t n_src, int32_t n_samples, int32_t rir_len, float* events_dev,
+                        float* mixture_dev, float* norm_dev, void* scratch_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

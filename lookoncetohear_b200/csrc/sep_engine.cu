@@ -62,6 +62,8 @@ struct SepEngine {
     __nv_bfloat16* planes = nullptr;
     int64_t planes_total = 0;
     bool cur_pdl = false;               // PDL attribute for the tensor-core launches of the chain being enqueued
+    bool fuse_ih = false;               // many sequences: W_ih + LayerNorm inside the tensor-core recurrence (option "fuse_ih").  Off:
+                                        // measured slower than GEMM + tc_lstm (offline B=16: 5.48 vs 4.50 ms per chain, profiles/r02i)
     bool use_tc = true;                 // rows > TC_MIN_ROWS: dense contractions on tcgen05 (option "tensor_cores")
     int tc_passes = 3;                  // 3 = bf16x3 split products (fp32 configs); 2 = bf16 weights x split activations (option
                                         // "bf16" = 1: the offline bf16 configuration); 1 = plain bf16 operands ("bf16" = 2)
@@ -322,6 +324,7 @@ static int set_attrs() {
     if (dev_ord < 0 || dev_ord >= 64) return fail(1, "device ordinal out of range");
     if (g_attr_done[dev_ord]) return 0;
     CK(cudaFuncSetAttribute(qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_SMEM));
+    CK(cudaFuncSetAttribute(qkv_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_MANY_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
@@ -356,6 +359,11 @@ constexpr int TCL_MIN_SEQDIRS = 2048;
 static cudaError_t lstm_any(SepEngine* e, const LstmArgs& l, cudaStream_t st, bool pdl) {
     if (e->use_tc && (int64_t)l.nseq * l.ndir >= TCL_MIN_SEQDIRS) return launch_tc_lstm(l, e->tc_passes, st, pdl);
     return launch_lstm_rec(l, st, pdl);
+}
+
+// ... and with enough sequences the input projection moves into the recurrence kernel too (tc_lstm_x_kernel)
+static bool tc_fused_lstm(const SepEngine* e, const LstmArgs& l) {
+    return e->use_tc && e->fuse_ih && (int64_t)l.nseq * l.ndir >= TCL_MIN_SEQDIRS;
 }
 
 // C[rows][N] = epi(LN?(A[rows][lda, first K]) W^T + bias) (+ R), plain row-major rows
@@ -444,19 +452,29 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         const BlockWeights& W = e->bw[b];
         // ---- intra: LN -> W_ih (both directions) -> BiLSTM over F -> Linear -> +res ------------
         GemmArgs g{};
-        if (tc) {
-            if (int rc = tc_rows_gemm(e, b, PL_IH1, X, 64, 64, 512, W.ln1_g, W.ln1_b, W.b1, nullptr, nullptr, GX, 512, rows, st)) return rc;
-        } else {
-            g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
-            g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
-            CK(launch_rows_gemm(g, st, pdl));
-        }
-        MARK("gemm_ih_intra");
         LstmArgs l{};
         l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
         l.nseq = B * T; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1;
         l.ndir = 2;
-        CK(lstm_any(e, l, st, pdl));
+        if (tc_fused_lstm(e, l)) {
+            // many sequences: LayerNorm, W_ih and the recurrence in ONE tensor-core kernel (no [rows x 512] projection in HBM)
+            tcl::LstmXArgs xa{};
+            xa.l = l; xa.x = X; xa.x_ld = 64;
+            xa.wih_hi = e->planes + e->plane_of[(size_t)b * PL_PER_BLOCK + PL_IH1]; xa.wih_lo = xa.wih_hi + e->planes_total;
+            xa.bias = W.b1; xa.ln_g = W.ln1_g; xa.ln_b = W.ln1_b;
+            CK(launch_tc_lstm_x(xa, e->tc_passes, st, false));
+            MARK("gemm_ih_intra");
+        } else {
+            if (tc) {
+                if (int rc = tc_rows_gemm(e, b, PL_IH1, X, 64, 64, 512, W.ln1_g, W.ln1_b, W.b1, nullptr, nullptr, GX, 512, rows, st)) return rc;
+            } else {
+                g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
+                g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
+                CK(launch_rows_gemm(g, st, pdl));
+            }
+            MARK("gemm_ih_intra");
+            CK(lstm_any(e, l, st, pdl));
+        }
         MARK("lstm_intra");
         if (tc_mid) {
             // many streams, one hop: the row-local middle of the block as four tensor-core GEMMs and the cell update.
@@ -512,15 +530,6 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             MARK("gemm_lin_intra");
             if (int rc = do_tap()) return rc;
             // ---- inter: LN -> W_ih -> LSTM over T with carried (h, c) -> Linear -> +res ------------
-            if (tc) {
-                if (int rc = tc_rows_gemm(e, b, PL_IH2, X, 64, 64, 256, W.ln2_g, W.ln2_b, W.b2, nullptr, nullptr, GX, 256, rows, st)) return rc;
-            } else {
-                g = GemmArgs{};
-                g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
-                g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
-                CK(launch_rows_gemm(g, st, pdl));
-            }
-            MARK("gemm_ih_inter");
             l = LstmArgs{};
             l.gx = GX; l.gx_ld = 256; l.out = Y; l.out_ld = 64; l.whh = W.whh2;
             l.h_state = sbase + ST_BLK + (int64_t)b * BK_STRIDE + BK_H;
@@ -528,7 +537,25 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             l.hc_outer_stride = ss;
             l.nseq = B * NF; l.L = T; l.inner_count = NF; l.outer_stride = (int64_t)T * NF; l.inner_stride = 1;
             l.step_stride = NF; l.ndir = 1;
-            CK(lstm_any(e, l, st, pdl));
+            if (tc_fused_lstm(e, l)) {
+                tcl::LstmXArgs xa{};
+                xa.l = l; xa.x = X; xa.x_ld = 64;
+                xa.wih_hi = e->planes + e->plane_of[(size_t)b * PL_PER_BLOCK + PL_IH2]; xa.wih_lo = xa.wih_hi + e->planes_total;
+                xa.bias = W.b2; xa.ln_g = W.ln2_g; xa.ln_b = W.ln2_b;
+                CK(launch_tc_lstm_x(xa, e->tc_passes, st, false));
+                MARK("gemm_ih_inter");
+            } else {
+                if (tc) {
+                    if (int rc = tc_rows_gemm(e, b, PL_IH2, X, 64, 64, 256, W.ln2_g, W.ln2_b, W.b2, nullptr, nullptr, GX, 256, rows, st)) return rc;
+                } else {
+                    g = GemmArgs{};
+                    g.A = X; g.lda = 64; g.Wt = W.wih2_t; g.bias = W.b2; g.C = GX; g.ldc = 256;
+                    g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; g.M = (int)rows; g.N = 256; g.K = 64;
+                    CK(launch_rows_gemm(g, st, pdl));
+                }
+                MARK("gemm_ih_inter");
+                CK(lstm_any(e, l, st, pdl));
+            }
             MARK("lstm_inter");
             if (tc) {
                 if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
@@ -550,8 +577,13 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (tc && !tc_mid) {      // Q|K|V projections of all rows as one tensor-core GEMM (+ bias + PReLU per column)
             if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
         }
-        CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
-                    (const float*)((tc || (fused_mid && !e->fold_mid_c)) ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
+        if (tc && (int64_t)B * T >= 296) {      // many frames: persistent form (LayerNorm parameters staged once per CTA)
+            CK(launch_k(pdl, qkv_many_kernel, dim3(296), dim3(QKV_THREADS), QKV_MANY_SMEM, st, (const float*)QKVRAW, Q, KALL, VALL, state, ss,
+                        b, W, T, B * T));
+        } else {
+            CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
+                        (const float*)((tc || (fused_mid && !e->fold_mid_c)) ? QKVRAW : nullptr), Q, KALL, VALL, state, ss, b, W, T, 0));
+        }
         MARK("qkv");
         if (nsplit > 1) {
             CK(launch_cluster(pdl, dim3(1, ATT_CL, 1), attn_cluster_kernel, dim3(T, NHEAD * ATT_CL, B), dim3(256), 0, st,
@@ -1279,6 +1311,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else if (n == "tensor_cores") e->use_tc = value != 0;
+    else if (n == "fuse_ih") e->fuse_ih = value != 0;
     else if (n == "bf16") e->tc_passes = value == 0 ? 3 : (value == 2 ? 1 : 2);   // 1: bf16 weights x split activations; 2: plain bf16 both
     else if (n == "graph_stats") e->graph_stats = value != 0;
     else return fail(2, "unknown option: " + n);

@@ -408,6 +408,112 @@ qkv_kernel(const float* __restrict__ X, const float* __restrict__ pre, float* __
 }
 
 // ------------------------------------------------------------------------------------------
+// K4a for MANY frames (offline batches, many streams) when the projections come from a tensor-core GEMM: the same
+// LayerNorm + head split + ring append as qkv_kernel, but persistent -- each CTA stages the LayerNorm parameters ONCE
+// (22 KB) and walks frames fi = blockIdx.x, + gridDim.x, ... with the 43 KB projection tile of the next frame in flight
+// (two TMA-filled buffers) while the 12 warps normalise the current one.  qkv_kernel's one-CTA-per-frame form costs
+// ~18 us per frame in staging latency (profiles/r02h); this form is bound by the 86 KB each frame moves.
+constexpr size_t QKV_MANY_SMEM = (size_t)(2 * NF * QKV_PLD + QKV_LNP) * sizeof(float);
+
+__global__ void __launch_bounds__(QKV_THREADS)
+qkv_many_kernel(const float* __restrict__ pre, float* __restrict__ Qbuf, float* __restrict__ Kall, float* __restrict__ Vall,
+                float* __restrict__ state, int64_t sstride, int blk, BlockWeights w, int T, int n_frames) {
+    extern __shared__ __align__(16) float sm[];
+    float* Pb[2] = {sm, sm + NF * QKV_PLD};
+    float* LNP = sm + 2 * NF * QKV_PLD;
+    __shared__ __align__(8) unsigned long long bars[3];
+    const int tid = threadIdx.x;
+    griddep_launch();
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) mbar_expect_tx(&bars[2], (unsigned)(QKV_LNP * 4));
+    __syncthreads();
+    if (tid < 6) {
+        const float* src = tid == 0 ? w.lnq_g : tid == 1 ? w.lnq_b : tid == 2 ? w.lnk_g : tid == 3 ? w.lnk_b : tid == 4 ? w.lnv_g : w.lnv_b;
+        float* dst = LNP + (tid < 4 ? tid * QK_LD : 4 * QK_LD + (tid - 4) * V_DIM);
+        tma_load_1d(dst, src, (tid < 4 ? QK_LD : V_DIM) * 4, &bars[2]);
+    }
+    griddep_wait();
+    const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
+    const long long pos0 = hdr->pos;
+    int fi = blockIdx.x;
+    if (fi < n_frames && tid == 0) {
+        mbar_expect_tx(&bars[0], NF * NQKV * 4);
+        tma_load_1d(Pb[0], pre + (int64_t)fi * NF * NQKV, NF * NQKV * 4, &bars[0]);
+    }
+    mbar_wait(&bars[2], 0);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int which = warp >> 2, h = warp & 3;
+    const int d = (which == 2) ? VD : QE;
+    const int n = NF * d;
+    const int col0 = (which == 2) ? (48 + h * VD) : (which * 24 + h * QE);
+    const int f0 = lane / d, e0 = lane % d, df = 32 / d, de = 32 % d;
+    const float* gam = LNP + (which == 0 ? 0 : (which == 1 ? 2 * QK_LD : 4 * QK_LD));
+    const float* bet = LNP + (which == 0 ? QK_LD : (which == 1 ? 3 * QK_LD : 4 * QK_LD + V_DIM));
+    const int ld = (which == 2) ? V_DIM : QK_LD;
+    unsigned it = 0;
+    for (; fi < n_frames; fi += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int nxt = fi + gridDim.x;
+        if (nxt < n_frames && tid == 0) {                  // the other buffer was released by the barrier that ended the previous frame
+            fence_proxy_async();
+            mbar_expect_tx(&bars[cur ^ 1], NF * NQKV * 4);
+            tma_load_1d(Pb[cur ^ 1], pre + (int64_t)nxt * NF * NQKV, NF * NQKV * 4, &bars[cur ^ 1]);
+        }
+        mbar_wait(&bars[cur], (it >> 1) & 1);
+        const float* P = Pb[cur];
+        const int b = fi / T, t = fi % T;
+        float s = 0.f;
+        {
+            int f = f0, e2 = e0;
+            for (int i = lane; i < n; i += 32) {
+                s += P[f * QKV_PLD + col0 + e2];
+                e2 += de; f += df;
+                if (e2 >= d) { e2 -= d; ++f; }
+            }
+        }
+        const float mu = warp_sum(s) / (float)n;
+        float q = 0.f;
+        {
+            int f = f0, e2 = e0;
+            for (int i = lane; i < n; i += 32) {
+                const float dv = P[f * QKV_PLD + col0 + e2] - mu;
+                q += dv * dv;
+                e2 += de; f += df;
+                if (e2 >= d) { e2 -= d; ++f; }
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) / (float)n + 1e-5f);
+        float* dst0 = nullptr;   // linear scratch / Q buffer
+        float* dst1 = nullptr;   // ring slot
+        const int64_t bh = (int64_t)b * NHEAD + h;
+        if (which == 0) {
+            dst0 = Qbuf + (bh * T + t) * QK_LD;
+        } else {
+            float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
+            const int slot = (int)((pos0 + t) % RING);
+            if (t >= T - ATT) dst1 = sb + (which == 1 ? BK_K : BK_V) + ((int64_t)h * RING + slot) * ld;
+            if (T > 1) dst0 = (which == 1 ? Kall : Vall) + (bh * (ATT - 1 + T) + (ATT - 1) + t) * ld;
+        }
+        {
+            int f = f0, e2 = e0;
+            for (int i = lane; i < n; i += 32) {
+                const float v = (P[f * QKV_PLD + col0 + e2] - mu) * rs * gam[i] + bet[i];
+                if (dst0) dst0[i] = v;
+                if (dst1) dst1[i] = v;
+                e2 += de; f += df;
+                if (e2 >= d) { e2 -= d; ++f; }
+            }
+        }
+        if (which != 2 && lane < 2) {        // zero the two pad columns of 582 -> 584
+            if (dst0) dst0[QK_DIM + lane] = 0.f;
+            if (dst1) dst1[QK_DIM + lane] = 0.f;
+        }
+        __syncthreads();                     // every warp is done with buffer `cur`: it may be refilled
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4b local attention: each query attends to its own frame + the 49 previous ones, unmasked
 // (tfgridnet_causal.py:564-581).  One CTA per (frame, head, stream): grid (T, 4, B), 256 threads.
 // T == 1: K/V rows are ring slots (frame n lives in slot n mod RING); T > 1: rows t .. t+49 of the
