@@ -242,7 +242,8 @@ mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict
 //   mid_b  g = GI + h W_hh ; (h, c) cell ; H' = h'            the serial stage: 64 KB of weights, K = 64
 //   mid_c  X2 = X1 + H' W_l2 + b ; P = PReLU(X2 W_qkv + b)   no carried state: runs on the qkv lanes
 __global__ void __launch_bounds__(256)
-mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ GI, BlockWeights w, int n_streams) {
+mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ GI, BlockWeights w, int n_streams,
+             int64_t hop_stride, int n_hops) {      // n_hops hops per launch: the buffers of hop j sit j * hop_stride floats further
     extern __shared__ __align__(16) float sm[];
     float* W1 = sm;                                   // intra linear, k-sliced
     float* W3a = W1 + (MID_W3A - MID_W1);             // W_ih, k-sliced
@@ -262,9 +263,12 @@ mid_a_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restri
     }
     __syncthreads();
     griddep_wait();
-    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
-        const int b = item / TILES;
-        const int r0 = (item % TILES) * MID_RT;
+    const float* Y0 = Y; float* X0 = X; float* GI0 = GI;
+    for (int item = blockIdx.x; item < n_hops * n_streams * TILES; item += gridDim.x) {
+        const int hop = item / (n_streams * TILES), it_h = item % (n_streams * TILES);
+        Y = Y0 + (int64_t)hop * hop_stride; X = X0 + (int64_t)hop * hop_stride; GI = GI0 + (int64_t)hop * hop_stride;
+        const int b = it_h / TILES;
+        const int r0 = (it_h % TILES) * MID_RT;
         const int nr = min(MID_RT, NF - r0);
         __syncthreads();
         const int64_t row0 = (int64_t)b * NF + r0;
@@ -386,7 +390,8 @@ mid_b_kernel(const float* __restrict__ GI, float* __restrict__ Hn, int64_t hop_s
 }
 
 __global__ void __launch_bounds__(256)
-mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restrict__ QKV, BlockWeights w, int n_streams) {
+mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restrict__ QKV, BlockWeights w, int n_streams,
+             int64_t hop_stride, int n_hops) {
     extern __shared__ __align__(16) float sm[];
     float* W5 = sm;                                   // inter linear | q|k|v projections, k-sliced
     float* W6 = W5 + (MID_W6 - MID_W5);
@@ -405,9 +410,12 @@ mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restr
     }
     __syncthreads();
     griddep_wait();
-    for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
-        const int b = item / TILES;
-        const int r0 = (item % TILES) * MID_RT;
+    const float* Hn0 = Hn; float* X0 = X; float* QKV0 = QKV;
+    for (int item = blockIdx.x; item < n_hops * n_streams * TILES; item += gridDim.x) {
+        const int hop = item / (n_streams * TILES), it_h = item % (n_streams * TILES);
+        Hn = Hn0 + (int64_t)hop * hop_stride; X = X0 + (int64_t)hop * hop_stride; QKV = QKV0 + (int64_t)hop * hop_stride;
+        const int b = it_h / TILES;
+        const int r0 = (it_h % TILES) * MID_RT;
         const int nr = min(MID_RT, NF - r0);
         __syncthreads();
         const int64_t row0 = (int64_t)b * NF + r0;

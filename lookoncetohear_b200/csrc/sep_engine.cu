@@ -84,6 +84,7 @@ struct SepEngine {
     std::vector<MidSrc> mid_src;   // per block: host offsets the packed mid_kernel weights are derived from at commit
     cudaStream_t pipe_streams[128] = {};
     std::vector<cudaEvent_t> pipe_events;
+    int64_t pipe_budget = 0; // bytes the pipelined workspace may take (min(24 GB, half of the free memory at first use))
     int pipe_frames = 0;     // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES); 0 = auto: as many as a 24 GB workspace holds
     int pipe_alanes = 12;    // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
     int pipe_midb_hops = 4;       // pipeline: consecutive hops one mid_b launch takes (<= PIPE_MIDB_MAX)
@@ -304,7 +305,7 @@ static Workspace carve(int n_blocks, int B, int T, uint32_t flags) {
     ws.PRE = alloc((int64_t)B * FC);
     ws.QKVRAW = alloc(rows * NQKV);
     ws.TAPS = alloc((flags & L2H_FLAG_TAPS) ? (int64_t)(1 + 3 * n_blocks) * rows * 64 : 0);
-    ws.total = cur;
+    ws.total = (cur + 511) & ~int64_t(511);      // a multiple of one GX row: pipelined hops address their slots as rows of one tensor
     return ws;
 }
 
@@ -437,9 +438,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         return 0;
     };
     float* sbase = state + sizeof(StateHeader) / 4;
-    const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS);
-    // measured (profiles/r02e): PDL on the tensor-core launches is slower (256 streams: 0.93 vs 0.87 ms per hop-step) -- a
-    // dependent CTA cannot become resident beside its predecessor (each holds ~200 KB of shared memory), so nothing overlaps
+    // programmatic dependent launch pays on the latency chain of a few rows; with many rows it is slower (256 streams: 0.939 vs
+    // 0.865 ms per hop-step, profiles/r02j_b256_options.jsonl): early-launched dependents park on the SMs the big kernels need
+    const bool pdl = e->use_pdl && a.prof == nullptr && !(flags & L2H_FLAG_TAPS) && !(e->use_tc && rows > TC_MIN_ROWS);
     e->cur_pdl = false;
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
@@ -504,12 +505,12 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             MARK("mid");
         } else if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
             float* GI = GX; float* HN = GX + rows * 256;         // the BiLSTM is done with GX
-            CK(launch_k(pdl, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st, (const float*)Y, X, GI, W, B));
+            CK(launch_k(pdl, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st, (const float*)Y, X, GI, W, B, (int64_t)0, 1));
             if (e->fold_mid_c) {
                 CK(launch_k(pdl, mid_b2_kernel, mid_grid_for(B, 2), dim3(256), MID_B2_SMEM, st, (const float*)GI, X, (int64_t)0, 1, state, ss, b, W, B));
             } else {
                 CK(launch_k(pdl, mid_b_kernel, mid_grid_for(B, 3), dim3(256), MID_B_SMEM, st, (const float*)GI, HN, (int64_t)0, 1, state, ss, b, W, B));
-                CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B));
+                CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B, (int64_t)0, 1));
             }
             MARK("mid");
         } else if (fused_mid) {
@@ -648,11 +649,16 @@ static int64_t pipe_slot_floats(SepEngine* e, int B) { return carve(e->n_blocks,
 // in flight owns a workspace slot (350 KB per stream), which is what bounds it for many streams
 static int pipe_frames_for(SepEngine* e, int B) {
     if (e->pipe_frames > 0) return e->pipe_frames;
-    const int64_t budget = (int64_t)24 << 30;
-    const int64_t fit = budget / (pipe_slot_floats(e, B) * (int64_t)sizeof(float));
+    // every hop in flight owns a workspace slot: at most 24 GB of them, and never more than half of what the device
+    // has free right now (the state, the caller's buffers and other tenants need room too)
+    if (e->pipe_budget == 0) {               // asked once per handle: cudaMemGetInfo costs tens of microseconds per call
+        e->pipe_budget = (int64_t)24 << 30;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0) e->pipe_budget = std::min<int64_t>(e->pipe_budget, (int64_t)(free_b / 2));
+    }
+    const int64_t fit = e->pipe_budget / (pipe_slot_floats(e, B) * (int64_t)sizeof(float));
     return (int)std::max<int64_t>(2, std::min<int64_t>(PIPE_MAX_FRAMES, fit));
 }
-
 static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_t origin) {
     if (e->n_blocks != 3) return fail(1, "pipeline graph is specialised to 3 blocks");
     const int B = a.B;
@@ -726,37 +732,45 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
         const int k1 = std::min(K, k0 + mb);                           // this batch: hops [k0, k1)
         for (int b = 0; b < 3; ++b) {
             const BlockWeights& W = e->bw[b];
-            // ---- stage A of every hop of the batch (parallel lanes) --------------------------------------
-            for (int k = k0; k < k1; ++k) {
-                float* wsp = a.wsp + (int64_t)k * slot;
+            // ---- stage A of the batch: ONE launch each of W_ih GEMM, BiLSTM and mid_a for its hops [k0, k1) (the hops'
+            // workspace slots are `slot` floats apart: strided rows / sequences / hop index inside the kernels) ------------
+            {
+                const int nh = k1 - k0;
+                float* wsp = a.wsp + (int64_t)k0 * slot;
                 float* X = wsp + ws.X; float* GX = wsp + ws.GX; float* Y = wsp + ws.Y;
-                cudaStream_t st_a = sA(b, k % e->pipe_alanes);
-                if (b == 0) {
-                    // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip
-                    // position the device derives from the state header)
-                    cudaStream_t sF = sFront(k);
-                    if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs,
-                                                         a.x_len, X, state, ss, e->w, 1, a.pos_rel, a.emb, PRE, k, K, k * HOP));
-                    if (int rc = edge(sF, st_a)) return rc;
-                } else {
-                    CK(cudaStreamWaitEvent(st_a, out_done[b - 1][k], 0));
+                cudaStream_t st_a = sA(b, (k0 / mb) % e->pipe_alanes);
+                for (int k = k0; k < k1; ++k) {
+                    if (b == 0) {
+                        // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip
+                        // position the device derives from the state header)
+                        cudaStream_t sF = sFront(k);
+                        if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs,
+                                                             a.x_len, a.wsp + (int64_t)k * slot + ws.X, state, ss, e->w, 1, a.pos_rel, a.emb, PRE, k, K, k * HOP));
+                        if (int rc = edge(sF, st_a)) return rc;
+                    } else {
+                        CK(cudaStreamWaitEvent(st_a, out_done[b - 1][k], 0));
+                    }
                 }
                 GemmArgs g{};
-                g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
-                g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows; g.N = 512; g.K = 64;
+                g.A = X; g.lda = 64; g.a_rows_per_seq = rows; g.a_seq_stride = slot;
+                g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512; g.c_rows_per_seq = rows; g.c_seq_stride = slot;
+                g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows * nh; g.N = 512; g.K = 64;
                 if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0));
                 LstmArgs l{};
                 l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
-                l.nseq = B; l.L = NF; l.inner_count = 1; l.outer_stride = NF; l.inner_stride = 0; l.step_stride = 1; l.ndir = 2;
+                l.nseq = B * nh; l.L = NF; l.inner_count = B; l.outer_stride = slot / 512; l.inner_stride = NF; l.step_stride = 1;
+                l.out_outer_stride = slot / 128; l.out_inner_stride = NF; l.out_step_stride = 1; l.ndir = 2;
                 if (!(e->pipe_skip & 4)) CK(launch_lstm_rec(l, st_a, (ppdl & 4) != 0));
                 // only the W_hh product + cell (mid_b) is serial per block; the rest rides on the parallel lanes.
                 // GI / H' live in the hop's GX slot, which the BiLSTM has finished with.
                 if (split_mid && !(e->pipe_skip & 8))
-                    CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid_for(B, 2), dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GX, W, B));
-                if (int rc = record(&a_done[b][k], st_a)) return rc;
+                    CK(launch_k((ppdl & 8) != 0, mid_a_kernel, mid_grid_for(B * nh, 2), dim3(256), MID_A_SMEM, st_a, (const float*)Y, X, GX, W, B, slot, nh));
+                cudaEvent_t ev_a;
+                if (int rc = record(&ev_a, st_a)) return rc;
+                for (int k = k0; k < k1; ++k) a_done[b][k] = ev_a;
             }
             // ---- the serial stage: one launch for the batch ----------------------------------------------------
-            for (int k = k0; k < k1; ++k) CK(cudaStreamWaitEvent(sB1(b), a_done[b][k], 0));
+            CK(cudaStreamWaitEvent(sB1(b), a_done[b][k0], 0));
             {
                 float* wsp = a.wsp + (int64_t)k0 * slot;
                 float* GI = wsp + ws.GX; float* HN = GI + (int64_t)rows * 256;
@@ -779,21 +793,22 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
             }
             cudaEvent_t midb_done;
             if (int rc = record(&midb_done, sB1(b))) return rc;
-            // ---- per hop: mid_c | qkv -> attention -> attn_out (parallel lanes with ring guards) -----------------
+            // ---- mid_c for the whole batch (one launch), then per hop: qkv -> attention -> attn_out (lanes, ring guards) ----
+            cudaEvent_t midc_done = midb_done;
+            if (split_mid && !fold) {
+                cudaStream_t st_c = sBc(b, k0 / mb);
+                float* wsp0 = a.wsp + (int64_t)k0 * slot;
+                CK(cudaStreamWaitEvent(st_c, midb_done, 0));
+                if (!(e->pipe_skip & 32))
+                    CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid_for(B * (k1 - k0), 4), dim3(256), MID_C_SMEM, st_c,
+                                (const float*)(wsp0 + ws.GX + (int64_t)rows * 256), wsp0 + ws.X, wsp0 + ws.QKVRAW, W, B, slot, k1 - k0));
+                if (int rc = record(&midc_done, st_c)) return rc;
+            }
             for (int k = k0; k < k1; ++k) {
                 float* wsp = a.wsp + (int64_t)k * slot;
                 float* X = wsp + ws.X; float* Z = wsp + ws.Z; float* Q = wsp + ws.Q; float* QKVRAW = wsp + ws.QKVRAW;
-                float* HN = wsp + ws.GX + (int64_t)rows * 256;
                 cudaStream_t st_q = sBq(b, k);
-                if (split_mid && !fold) {   // mid_c on its own lanes: the qkv lanes are held back by the ring guard
-                    cudaStream_t st_c = sBc(b, k);
-                    CK(cudaStreamWaitEvent(st_c, midb_done, 0));
-                    if (!(e->pipe_skip & 32))
-                        CK(launch_k((ppdl & 32) != 0, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st_c, (const float*)HN, X, QKVRAW, W, B));
-                    if (int rc = edge(st_c, st_q)) return rc;
-                } else {
-                    CK(cudaStreamWaitEvent(st_q, midb_done, 0));
-                }
+                CK(cudaStreamWaitEvent(st_q, midc_done, 0));
                 // the ring row this hop's K/V overwrite was last read by the attention of hop k-3: it and every earlier
                 // attention (one per attention lane) must be done
                 for (int d = 0; d < e->pipe_tlanes && k - PIPE_QKV_AHEAD - 1 - d >= 0; ++d)

@@ -264,8 +264,9 @@ def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
 
 def test_launch_counter_counts_graph_nodes(model, dev):
     """bench.py's gpu_launches comes from l2h_sep_launch_count: a replayed CUDA graph counts its kernel nodes.  One
-    sequential hop = 1 front + 3 x 6 + 1 back = 20 kernels; a pipelined 8-hop stream = 8 x 23 + one mid_b launch per block
-    and 4 hops + the header advance + the clip-base kernel."""
+    sequential hop = 1 front + 3 x 6 + 1 back = 20 kernels; a pipelined 8-hop stream = per hop front + back + 3 x (qkv, attention,
+    attn_out), per block and 4-hop batch ONE launch each of W_ih GEMM, BiLSTM, mid_a, mid_b, mid_c, + the header advance + the
+    clip-base kernel = 120 (15 kernels per hop; the per-hop stage A and mid_c of round 1 made it 23.75)."""
     import ctypes
     from lookoncetohear_b200 import _cabi
     net, _ = model
@@ -284,7 +285,8 @@ def test_launch_counter_counts_graph_nodes(model, dev):
     net.stream_dev(x.to(dev), e, chunks_per_call=1, state=st, n_calls=8)
     torch.cuda.synchronize()
     _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
-    assert n.value == 8 * 23 + 3 * 2 + 1 + 1
+    # per hop: front, back, 3 x (qkv, attention, attn_out); per 4-hop batch and block: W_ih GEMM, BiLSTM, mid_a, mid_b, mid_c
+    assert n.value == 8 * 11 + 2 * 3 * 5 + 1 + 1
 
 
 def test_fold_mid_c_option(model, dev):
