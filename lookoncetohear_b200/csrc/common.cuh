@@ -140,12 +140,34 @@ struct TraceScope {
                 unsigned int sm;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
                 rec->ptr = (unsigned long long)ptr; rec->kernel = (unsigned int)kernel; rec->sm = sm; rec->t1 = 0;
+                unsigned long long* m = marks();
+                for (int p = 0; p < TRACE_MARKS; ++p) m[p] = 0ull;
                 rec->t0 = globaltimer_ns();
             }
         }
     }
     __device__ __forceinline__ ~TraceScope() {
-        if (rec != nullptr) rec->t1 = globaltimer_ns();
+        if (rec != nullptr) {
+            rec->t1 = globaltimer_ns();
+            unsigned long long* m = marks();
+            for (int p = 0; p < TRACE_MARKS; ++p) {      // time stamps taken inside the kernel: one more record each, kernel id 100 + point
+                if (m[p] == 0ull) continue;
+                const unsigned int slot = atomicAdd(&g_trace_n, 1u);
+                if (slot < g_trace_cap) {
+                    TraceRec* r = g_trace + slot;
+                    r->ptr = rec->ptr; r->kernel = 100u + (unsigned int)p; r->sm = rec->sm; r->t0 = r->t1 = m[p];
+                }
+            }
+        }
+    }
+    static constexpr int TRACE_MARKS = 16;
+    static __device__ __forceinline__ unsigned long long* marks() {
+        __shared__ unsigned long long m[TRACE_MARKS];
+        return m;
+    }
+    // a time stamp inside the kernel (the recording thread only; kept in shared memory until the kernel ends)
+    __device__ __forceinline__ void mark(int point) {
+        if (rec != nullptr) marks()[point] = globaltimer_ns();
     }
 };
 

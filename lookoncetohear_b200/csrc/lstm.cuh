@@ -138,6 +138,7 @@ lstm_rec3_kernel(const LstmArgs a) {
 
     const float LOG2E = 1.4426950408889634f;
     const float S0 = kh ? -2.f * LOG2E : -LOG2E, A0 = kh ? 2.f : 1.f, B0 = kh ? -1.f : 0.f;
+    trace_.mark(0);
 
     int cur = 0;
     for (int it = 0; it < a.L; ++it) {
@@ -185,6 +186,7 @@ lstm_rec3_kernel(const LstmArgs a) {
         if (!PRE && (it & 3) == 3) cp_async_wait<0>();    // the next four rows (issued 4 steps ago) have landed
         __syncthreads();
     }
+    trace_.mark(1);
     if (a.h_state != nullptr) {
 #pragma unroll
         for (int s = 0; s < NSEQ; ++s) {

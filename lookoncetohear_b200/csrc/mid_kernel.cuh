@@ -110,128 +110,152 @@ __device__ __forceinline__ void mid_mm(const float* __restrict__ Wp, const float
     lane_reduce_scatter<MID_RT * C, KQ>(v, kq);
 }
 
+// Shared-memory tiles of one mid section (carved from the dynamic shared memory after the packed weights)
+struct MidSmem {
+    float *Wp, *A1, *A3, *A3h, *A5, *A6, *x1s;
+    __device__ __forceinline__ explicit MidSmem(float* sm)
+        : Wp(sm), A1(sm + MID_PACK), A3(A1 + MID_A1), A3h(A3 + MID_A3), A5(A3h + MID_A3), A6(A5 + MID_A5), x1s(A6 + MID_A6) {}
+};
+
+// The section's small parameter vectors, staged in shared memory before the dependency wait: every one of them would
+// otherwise be a first-touch global load in the middle of the tile's latency chain (6 exposed L2 round trips per tile).
+constexpr int MV_BL1 = 0, MV_LN2G = 64, MV_LN2B = 128, MV_B2 = 192, MV_BL2 = 448, MV_BQKV = 512, MV_SLOPES = 624, MV_TOTAL = 628;
+__device__ __forceinline__ void mid_stage_vecs(float* vs, const BlockWeights& w, int tid) {
+    for (int i = tid; i < MV_TOTAL; i += 256) {
+        const float* src = i < MV_LN2G ? w.bl1 + i : i < MV_LN2B ? w.ln2_g + (i - MV_LN2G) : i < MV_B2 ? w.ln2_b + (i - MV_LN2B)
+                         : i < MV_BL2 ? w.b2 + (i - MV_B2) : i < MV_BQKV ? w.bl2 + (i - MV_BL2) : i < MV_SLOPES ? w.bqkv + (i - MV_BQKV)
+                         : w.slopes + (i - MV_SLOPES);
+        vs[i] = __ldg(src);
+    }
+}
+
+// One tile of MID_RT rows through the whole section.  Yrows/Xin: the tile's rows of the BiLSTM output / the block input
+// (global); X2out / Pout: where the tile's rows of X2 (row stride 64) and of the projections (row stride NQKV) go --
+// global for mid_kernel, the caller's shared memory for tail_kernel (hop_kernels.cuh); Xin may alias X2out.
+// hst/cst: the stream's carried (h, c) of this block, [97][64].  vs: the vectors staged by mid_stage_vecs (visible to all
+// threads after the first barrier in here).  The caller has waited for the weights.
+__device__ __forceinline__ void mid_tile(const MidSmem& S, const float* Yrows, const float* Xin, float* X2out, float* Pout,
+                                         float* hst, float* cst, int r0, int nr, const float* vs, int tid) {
+    float* Wp = S.Wp; float* A1 = S.A1; float* A3 = S.A3; float* A3h = S.A3h; float* A5 = S.A5; float* A6 = S.A6; float* x1s = S.x1s;
+    // ---- tile loads: Y -> A1, h -> A3h ------------------------------------------------------------
+    {
+        const int r = tid >> 5, k4 = tid & 31;
+        const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Yrows + (int64_t)r * 128 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        A1[mid_aidx(M1_KS, k4 * 4 + 0, r)] = v.x; A1[mid_aidx(M1_KS, k4 * 4 + 1, r)] = v.y;
+        A1[mid_aidx(M1_KS, k4 * 4 + 2, r)] = v.z; A1[mid_aidx(M1_KS, k4 * 4 + 3, r)] = v.w;
+    }
+    if (tid < 128) {
+        const int r = tid >> 4, k4 = tid & 15;
+        const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        A3h[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; A3h[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
+        A3h[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; A3h[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
+    }
+    // the two other chain inputs of this thread, requested now: the residual of phase 1 and the cell state of phase 4
+    const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
+    const float2 xo = (r1 < nr) ? *reinterpret_cast<const float2*>(Xin + (int64_t)r1 * 64 + n1) : make_float2(0.f, 0.f);
+    const float2 cold = ((tid & 7) < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + (tid & 7)) * 64 + (tid >> 3) * 2) : make_float2(0.f, 0.f);
+    __syncthreads();
+    // ---- phase 1: X1 = X + Y W1 + b ;  lane (cg, kq) finishes row kq/2, columns cg*4 + (kq&1)*2 + {0,1}
+    float2 x1v;
+    {
+        float v[MID_RT * M1_C];
+        mid_mm<M1_C, M1_KQ, M1_KS, M1_N>(Wp + MID_W1, A1, tid >> 4, tid & 15, v);
+        const float2 bias = *reinterpret_cast<const float2*>(vs + MV_BL1 + n1);
+        x1v = make_float2(xo.x + v[0] + bias.x, xo.y + v[1] + bias.y);
+        *reinterpret_cast<float2*>(x1s + r1 * 64 + n1) = x1v;
+    }
+    __syncthreads();
+    // ---- phase 2: LayerNorm over channels, one warp per row -> A3 ------------------------------------
+    {
+        const int r = tid >> 5, lane = tid & 31;
+        const float v0 = x1s[r * 64 + lane], v1 = x1s[r * 64 + lane + 32];
+        const float mu = warp_sum(v0 + v1) * (1.f / 64.f);
+        const float d0 = v0 - mu, d1 = v1 - mu;
+        const float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
+        A3[mid_aidx(M3_KS, lane, r)] = d0 * rs * vs[MV_LN2G + lane] + vs[MV_LN2B + lane];
+        A3[mid_aidx(M3_KS, lane + 32, r)] = d1 * rs * vs[MV_LN2G + lane + 32] + vs[MV_LN2B + lane + 32];
+    }
+    __syncthreads();
+    // ---- phase 3 + 4: gates and LSTM cell; lane (jp, kq) finishes row kq, hidden units 2jp, 2jp+1 ----
+    {
+        // two K = 64 products, combined as (x W_ih + b) + h W_hh: the arithmetic of mid_a_kernel + mid_b_kernel
+        float u[MID_RT * M3_C], v[MID_RT * M3_C];
+        const int jp = tid >> 3, r = tid & 7;
+        mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3A, A3, jp, r, u);
+        mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3B, A3h, jp, r, v);
+        const float4 ba = *reinterpret_cast<const float4*>(vs + MV_B2 + jp * 8);
+        const float4 bb = *reinterpret_cast<const float4*>(vs + MV_B2 + jp * 8 + 4);
+        const float4 ga = make_float4(u[0] + ba.x, u[1] + ba.y, u[2] + ba.z, u[3] + ba.w);
+        const float4 gb = make_float4(u[4] + bb.x, u[5] + bb.y, u[6] + bb.z, u[7] + bb.w);
+        const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
+        const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
+        const float c0 = gf0 * cold.x + gi0 * gg0, c1 = gf1 * cold.y + gi1 * gg1;
+        const float h0 = go0 * fast_tanh(c0), h1 = go1 * fast_tanh(c1);
+        if (r < nr) {
+            *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = make_float2(c0, c1);
+            *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = make_float2(h0, h1);
+        }
+        A5[mid_aidx(M5_KS, jp * 2, r)] = h0;
+        A5[mid_aidx(M5_KS, jp * 2 + 1, r)] = h1;
+    }
+    __syncthreads();
+    // ---- phase 5: X2 = X1 + h' W_l2 + b ; same lane -> output mapping as phase 1 -------------------
+    {
+        float v[MID_RT * M5_C];
+        mid_mm<M5_C, M5_KQ, M5_KS, M5_N>(Wp + MID_W5, A5, tid >> 4, tid & 15, v);
+        const float2 bias = *reinterpret_cast<const float2*>(vs + MV_BL2 + n1);
+        const float2 x2v = make_float2(x1v.x + v[0] + bias.x, x1v.y + v[1] + bias.y);
+        if (r1 < nr) *reinterpret_cast<float2*>(X2out + (int64_t)r1 * 64 + n1) = x2v;
+        A6[mid_aidx(M6_KS, n1, r1)] = x2v.x;
+        A6[mid_aidx(M6_KS, n1 + 1, r1)] = x2v.y;
+    }
+    __syncthreads();
+    // ---- phase 6: P = PReLU(X2 W_qkv + b); lane (cg < 28, kq) finishes row kq, columns cg*4 .. +3 ----
+    if (tid < (M6_N / M6_C) * M6_KQ) {
+        float v[MID_RT * M6_C];
+        const int cg = tid >> 3, r = tid & 7;
+        mid_mm<M6_C, M6_KQ, M6_KS, M6_N>(Wp + MID_W6, A6, cg, r, v);
+        const float4 bias = *reinterpret_cast<const float4*>(vs + MV_BQKV + cg * 4);
+        const float slope = vs[MV_SLOPES + (cg < 6 ? 0 : (cg < 12 ? 1 : 2))];
+        if (r < nr)
+            *reinterpret_cast<float4*>(Pout + (int64_t)r * NQKV + cg * 4) =
+                make_float4(prelu(v[0] + bias.x, slope), prelu(v[1] + bias.y, slope), prelu(v[2] + bias.z, slope),
+                            prelu(v[3] + bias.w, slope));
+    }
+}
+
 __global__ void __launch_bounds__(256)
-mid_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ QKV, float* __restrict__ state,
+mid_kernel(const float* __restrict__ Y, float* X, float* __restrict__ QKV, float* __restrict__ state,
            int64_t sstride, int blk, BlockWeights w, int n_streams) {
     extern __shared__ __align__(16) float sm[];
-    float* Wp = sm;                       // the packed weights (BlockWeights::mid_pack)
-    float* A1 = Wp + MID_PACK;            // intra LSTM outputs Y, k-sliced for phase 1
-    float* A3 = A1 + MID_A1;              // LN(X1), k-sliced for phase 3
-    float* A3h = A3 + MID_A3;             // h, k-sliced for phase 3
-    float* A5 = A3h + MID_A3;             // h', k-sliced for phase 5
-    float* A6 = A5 + MID_A5;              // X2, k-sliced for phase 6
-    float* x1s = A6 + MID_A6;             // [RT][64] X1 (LayerNorm input)
-
+    const MidSmem S(sm);
     __shared__ __align__(8) unsigned long long wbar;
+    __shared__ __align__(16) float vs[MV_TOTAL];
     TraceScope trace_(TK_MID, Y);
     griddep_launch();
     const int tid = threadIdx.x;
     constexpr int TILES = (NF + MID_RT - 1) / MID_RT;       // row tiles per stream
+    mid_stage_vecs(vs, w, tid);
     // ---- weights -> smem: TMA bulk copies (independent of the chain, so issued before the wait) ------
     if (tid == 0) {
         mbar_init(&wbar, 1);
         mbar_fence_init();
         mbar_expect_tx(&wbar, MID_PACK * 4);
-        tma_load_1d(Wp + MID_W1, w.mid_pack + MID_W1, (MID_W3B - MID_W1) * 4, &wbar);
-        tma_load_1d(Wp + MID_W3B, w.mid_pack + MID_W3B, (MID_W5 - MID_W3B) * 4, &wbar);
-        tma_load_1d(Wp + MID_W5, w.mid_pack + MID_W5, (MID_PACK - MID_W5) * 4, &wbar);
+        tma_load_1d(S.Wp + MID_W1, w.mid_pack + MID_W1, (MID_W3B - MID_W1) * 4, &wbar);
+        tma_load_1d(S.Wp + MID_W3B, w.mid_pack + MID_W3B, (MID_W5 - MID_W3B) * 4, &wbar);
+        tma_load_1d(S.Wp + MID_W5, w.mid_pack + MID_W5, (MID_PACK - MID_W5) * 4, &wbar);
     }
     __syncthreads();
     griddep_wait();
+    mbar_wait(&wbar, 0);
     for (int item = blockIdx.x; item < n_streams * TILES; item += gridDim.x) {
         const int b = item / TILES;
         const int r0 = (item % TILES) * MID_RT;
         const int nr = min(MID_RT, NF - r0);
         __syncthreads();                    // the previous item's tiles are fully consumed
         float* sb = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride + ST_BLK + (int64_t)blk * BK_STRIDE;
-        float* hst = sb + BK_H;
-        float* cst = sb + BK_C;
         const int64_t row0 = (int64_t)b * NF + r0;
-        // ---- tile loads: Y -> A1, h -> A3h ------------------------------------------------------------
-        {
-            const int r = tid >> 5, k4 = tid & 31;
-            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(Y + (row0 + r) * 128 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            A1[mid_aidx(M1_KS, k4 * 4 + 0, r)] = v.x; A1[mid_aidx(M1_KS, k4 * 4 + 1, r)] = v.y;
-            A1[mid_aidx(M1_KS, k4 * 4 + 2, r)] = v.z; A1[mid_aidx(M1_KS, k4 * 4 + 3, r)] = v.w;
-        }
-        if (tid < 128) {
-            const int r = tid >> 4, k4 = tid & 15;
-            const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            A3h[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; A3h[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
-            A3h[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; A3h[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
-        }
-        mbar_wait(&wbar, 0);
-        __syncthreads();
-        // ---- phase 1: X1 = X + Y W1 + b ;  lane (cg, kq) finishes row kq/2, columns cg*4 + (kq&1)*2 + {0,1}
-        float2 x1v;
-        const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
-        {
-            float v[MID_RT * M1_C];
-            mid_mm<M1_C, M1_KQ, M1_KS, M1_N>(Wp + MID_W1, A1, tid >> 4, tid & 15, v);
-            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl1 + n1));
-            const float2 xo = (r1 < nr) ? *reinterpret_cast<const float2*>(X + (row0 + r1) * 64 + n1) : make_float2(0.f, 0.f);
-            x1v = make_float2(xo.x + v[0] + bias.x, xo.y + v[1] + bias.y);
-            *reinterpret_cast<float2*>(x1s + r1 * 64 + n1) = x1v;
-        }
-        __syncthreads();
-        // ---- phase 2: LayerNorm over channels, one warp per row -> A3 ------------------------------------
-        {
-            const int r = tid >> 5, lane = tid & 31;
-            const float v0 = x1s[r * 64 + lane], v1 = x1s[r * 64 + lane + 32];
-            const float mu = warp_sum(v0 + v1) * (1.f / 64.f);
-            const float d0 = v0 - mu, d1 = v1 - mu;
-            const float rs = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + 1e-5f);
-            A3[mid_aidx(M3_KS, lane, r)] = d0 * rs * __ldg(w.ln2_g + lane) + __ldg(w.ln2_b + lane);
-            A3[mid_aidx(M3_KS, lane + 32, r)] = d1 * rs * __ldg(w.ln2_g + lane + 32) + __ldg(w.ln2_b + lane + 32);
-        }
-        __syncthreads();
-        // ---- phase 3 + 4: gates and LSTM cell; lane (jp, kq) finishes row kq, hidden units 2jp, 2jp+1 ----
-        {
-            // two K = 64 products, combined as (x W_ih + b) + h W_hh: the arithmetic of mid_a_kernel + mid_b_kernel
-            float u[MID_RT * M3_C], v[MID_RT * M3_C];
-            const int jp = tid >> 3, r = tid & 7;
-            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3A, A3, jp, r, u);
-            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3B, A3h, jp, r, v);
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(w.b2 + jp * 8 + 4));
-            const float4 ga = make_float4(u[0] + ba.x, u[1] + ba.y, u[2] + ba.z, u[3] + ba.w);
-            const float4 gb = make_float4(u[4] + bb.x, u[5] + bb.y, u[6] + bb.z, u[7] + bb.w);
-            const float2 cold = (r < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + r) * 64 + jp * 2) : make_float2(0.f, 0.f);
-            const float gi0 = fast_sigmoid(v[0] + ga.x), gf0 = fast_sigmoid(v[1] + ga.y), gg0 = fast_tanh(v[2] + ga.z), go0 = fast_sigmoid(v[3] + ga.w);
-            const float gi1 = fast_sigmoid(v[4] + gb.x), gf1 = fast_sigmoid(v[5] + gb.y), gg1 = fast_tanh(v[6] + gb.z), go1 = fast_sigmoid(v[7] + gb.w);
-            const float c0 = gf0 * cold.x + gi0 * gg0, c1 = gf1 * cold.y + gi1 * gg1;
-            const float h0 = go0 * fast_tanh(c0), h1 = go1 * fast_tanh(c1);
-            if (r < nr) {
-                *reinterpret_cast<float2*>(cst + (r0 + r) * 64 + jp * 2) = make_float2(c0, c1);
-                *reinterpret_cast<float2*>(hst + (r0 + r) * 64 + jp * 2) = make_float2(h0, h1);
-            }
-            A5[mid_aidx(M5_KS, jp * 2, r)] = h0;
-            A5[mid_aidx(M5_KS, jp * 2 + 1, r)] = h1;
-        }
-        __syncthreads();
-        // ---- phase 5: X2 = X1 + h' W_l2 + b ; same lane -> output mapping as phase 1 -------------------
-        {
-            float v[MID_RT * M5_C];
-            mid_mm<M5_C, M5_KQ, M5_KS, M5_N>(Wp + MID_W5, A5, tid >> 4, tid & 15, v);
-            const float2 bias = __ldg(reinterpret_cast<const float2*>(w.bl2 + n1));
-            const float2 x2v = make_float2(x1v.x + v[0] + bias.x, x1v.y + v[1] + bias.y);
-            if (r1 < nr) *reinterpret_cast<float2*>(X + (row0 + r1) * 64 + n1) = x2v;
-            A6[mid_aidx(M6_KS, n1, r1)] = x2v.x;
-            A6[mid_aidx(M6_KS, n1 + 1, r1)] = x2v.y;
-        }
-        __syncthreads();
-        // ---- phase 6: P = PReLU(X2 W_qkv + b); lane (cg < 28, kq) finishes row kq, columns cg*4 .. +3 ----
-        if (tid < (M6_N / M6_C) * M6_KQ) {
-            float v[MID_RT * M6_C];
-            const int cg = tid >> 3, r = tid & 7;
-            mid_mm<M6_C, M6_KQ, M6_KS, M6_N>(Wp + MID_W6, A6, cg, r, v);
-            const float4 bias = __ldg(reinterpret_cast<const float4*>(w.bqkv + cg * 4));
-            const float slope = __ldg(w.slopes + (cg < 6 ? 0 : (cg < 12 ? 1 : 2)));
-            if (r < nr)
-                *reinterpret_cast<float4*>(QKV + (row0 + r) * NQKV + cg * 4) =
-                    make_float4(prelu(v[0] + bias.x, slope), prelu(v[1] + bias.y, slope), prelu(v[2] + bias.z, slope),
-                                prelu(v[3] + bias.w, slope));
-        }
+        mid_tile(S, Y + row0 * 128, X + row0 * 64, X + row0 * 64, QKV + row0 * NQKV, sb + BK_H, sb + BK_C, r0, nr, vs, tid);
     }
 }
 

@@ -21,6 +21,7 @@
 #include "lstm.cuh"
 #include "sep_kernels.cuh"
 #include "mid_kernel.cuh"
+#include "hop_kernels.cuh"
 
 namespace l2h {
 
@@ -101,6 +102,7 @@ struct SepEngine {
     bool fold_mid_c = false;      // no mid_c / no projection in the mid kernels: Linear in mid_b2, Q/K/V projection in qkv (untested)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
+    bool use_tail = true;    // one-hop calls of a few streams: mid + qkv + attention + attn_out (+ next W_ih) as ONE 16-CTA cluster kernel (option "fused_tail")
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
 };
 
@@ -319,6 +321,7 @@ static inline bool mid_split_for_throughput(int B) { return mid_items(B) > 148; 
 
 // cudaFuncSetAttribute applies to the CURRENT device: keep one flag per device ordinal
 static bool g_attr_done[64] = {};
+static int g_tail_clusters[64] = {};     // how many 16-CTA tail_kernel clusters the device can hold at once (0: cannot be scheduled)
 static int set_attrs() {
     int dev_ord = 0;
     CK(cudaGetDevice(&dev_ord));
@@ -339,6 +342,22 @@ static int set_attrs() {
     CK(configure_lstm());
     CK(umma::configure());
     CK(configure_tc_lstm());
+    CK(cudaFuncSetAttribute(front1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT1_SMEM));
+    {   // tail_kernel: 16 CTAs per cluster is a non-portable size; ask whether this device can place it
+        g_tail_clusters[dev_ord] = 0;
+        if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM) == cudaSuccess &&
+            cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(TAIL_CL, 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = TAIL_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = TAIL_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, tail_kernel, &cfg) == cudaSuccess) g_tail_clusters[dev_ord] = ncl;
+        }
+        cudaGetLastError();
+    }
     g_attr_done[dev_ord] = true;
     return 0;
 }
@@ -429,6 +448,13 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     // many rows (whole utterances, offline batches, many streams): the dense contractions run on the tensor cores
     const bool tc = e->use_tc && rows > TC_MIN_ROWS;
     const bool tc_mid = tc && T == 1 && !(flags & L2H_FLAG_TAPS);
+    // few streams, one hop (the latency path): everything after the BiLSTM as one cluster kernel per stream
+    bool fused_tail = false;
+    if (fused_mid && !tc && e->use_tail && !e->fold_mid_c) {
+        int dev_ord = 0;
+        CK(cudaGetDevice(&dev_ord));
+        fused_tail = B <= g_tail_clusters[dev_ord];      // all clusters of the launch resident at once
+    }
     int tap = 0;
     auto do_tap = [&]() -> int {
         if (flags & L2H_FLAG_TAPS) {
@@ -444,8 +470,13 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     e->cur_pdl = false;
 #define MARK(name) do { if (a.prof) { if (int _rc = a.prof->mark(name, st)) return _rc; } } while (0)
     MARK("start");
-    CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
-                a.pos_rel, emb, PRE, 0, 1, 0));
+    if (fused_tail) {      // the frame as 13 row tiles: spectrum of the tile's bins, conv, and block 0's input projection
+        CK(launch_k(false, front1_kernel, dim3(TAIL_TILES + 1, B), dim3(256), FRONT1_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w,
+                    e->bw[0], GX, a.pos_rel, emb, PRE));
+    } else {
+        CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
+                    a.pos_rel, emb, PRE, 0, 1, 0));
+    }
     MARK("front");
     if (int rc = do_tap()) return rc;
 
@@ -466,7 +497,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             CK(launch_tc_lstm_x(xa, e->tc_passes, st, false));
             MARK("gemm_ih_intra");
         } else {
-            if (tc) {
+            if (fused_tail) {
+                // front1_kernel (block 0) / the previous block's tail_kernel (its phase G) already wrote this block's input projection
+            } else if (tc) {
                 if (int rc = tc_rows_gemm(e, b, PL_IH1, X, 64, 64, 512, W.ln1_g, W.ln1_b, W.b1, nullptr, nullptr, GX, 512, rows, st)) return rc;
             } else {
                 g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
@@ -513,6 +546,17 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                 CK(launch_k(pdl, mid_c_kernel, mid_grid_for(B, 4), dim3(256), MID_C_SMEM, st, (const float*)HN, X, QKVRAW, W, B, (int64_t)0, 1));
             }
             MARK("mid");
+        } else if (fused_tail) {
+            NextIh nx{};
+            if (b + 1 < e->n_blocks) {
+                const BlockWeights& Wn = e->bw[b + 1];
+                nx.ln_g = Wn.ln1_g; nx.ln_b = Wn.ln1_b; nx.wih_t = Wn.wih1_t; nx.bias = Wn.b1; nx.GX = GX;
+            }
+            CK(launch_cluster(pdl, dim3(TAIL_CL, 1, 1), tail_kernel, dim3(TAIL_CL, B), dim3(256), TAIL_SMEM, st, (const float*)Y, X, state, ss,
+                              b, W, nx, (b == 0 && e->n_blocks > 1) ? 1 : 0, 0));
+            MARK("tail");
+            if (int rc = do_tap()) return rc;
+            continue;
         } else if (fused_mid) {
             if (e->fold_mid_c)
                 CK(launch_k(pdl, mid_noproj_kernel, mid_grid_for(B, 1), dim3(256), MID_SMEM, st, (const float*)Y, X, QKVRAW, state, ss, b, W, B));
@@ -1152,7 +1196,12 @@ int l2h_sep_launches_per_forward(void* handle, int32_t frames, int32_t* n) {
     // streams, where the mid section runs as three kernels), a multi-hop call 10.  Streams of one-hop calls go through
     // the pipelined graph instead -- l2h_sep_launch_count has the exact figure for everything this handle launched.
     const int one_hop = e->use_mid ? 6 : 9;
-    *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
+    int dev_ord = 0;
+    cudaGetDevice(&dev_ord);
+    if (frames == 1 && e->use_mid && e->use_tail && !e->fold_mid_c && dev_ord >= 0 && dev_ord < 64 && g_tail_clusters[dev_ord] > 0)
+        *n = 1 + e->n_blocks * 2 + 1;       // front1, (BiLSTM, tail_kernel) per block, back
+    else
+        *n = 1 + e->n_blocks * (frames == 1 ? one_hop : 10) + 1;
     return 0;
 }
 
@@ -1323,6 +1372,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "pipeline_back_lanes") e->pipe_blanes = std::max(1, std::min(PIPE_BLANES, (int)value));
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
+    else if (n == "fused_tail") e->use_tail = value != 0;
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else if (n == "tensor_cores") e->use_tc = value != 0;

@@ -128,6 +128,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
         xs[m][n] = (s >= 0 && s < x_len) ? x[(int64_t)b * x_bstride + (int64_t)m * x_cstride + s] : 0.f;
     }
     __syncthreads();
+    trace_.mark(0);
     // history frames from conv_buf: frame -2 -> slot 0, frame -1 -> slot 1
     for (int i = 0; i < 2; ++i) {
         const int g = gi - 2 + i;               // frame index in the group; < 0: before the group -> conv_buf
@@ -139,6 +140,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
 #pragma unroll
         for (int i = 0; i < 3; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
         mbar_wait(&wbar, 0);
+        trace_.mark(1);
 #pragma unroll 8
         for (int n = 0; n < NFFT; ++n) {
             const float wv = wat_s[n * 196 + tid];
@@ -158,6 +160,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
         }
     }
     __syncthreads();
+    trace_.mark(2);
     // conv: X[f][o] = b_o + sum_{c,i,j} Wc[o][c][i][j] * U[i][c][f-1+j]
     {
         const int o = tid & 63, fg = tid >> 6;
@@ -176,6 +179,7 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
             X[(((int64_t)b * T + t) * NF + f) * CH + o] = acc;
         }
     }
+    trace_.mark(3);
     // next conv_buf = spectrogram rows of the last two frames of the group, written by its last frame
     if (gi == GN - 1) {
         for (int e = tid; e < 4 * NF; e += 256) {
@@ -994,6 +998,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     }
     __syncthreads();
     griddep_wait();
+    trace_.mark(0);
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
     const int soff = sample_off + (pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0);
@@ -1019,6 +1024,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
         }
     }
     mbar_wait(&bars[0], 0);
+    trace_.mark(1);
     // deconv of the own bins for frames t (fi = 1) and, when it is inside this call, t-1 (fi = 0)
     {
         const int warp = tid >> 5, lane = tid & 31;
@@ -1061,6 +1067,7 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
         }
     }
     __syncthreads();                        // R (own bins) complete
+    trace_.mark(2);
     // synthesis over the own filter rows: w_t[n] (n < 128) from R_t, w_{t-1}[n] (n >= 128) from R_{t-1}
     mbar_wait(&bars[1], 0);
 #pragma unroll
@@ -1084,7 +1091,9 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
             const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
             ib_next[idx] = R[NSRC * NROW + idx];
         }
+    trace_.mark(3);
     cluster.sync();                         // all four partial windows are complete and visible cluster-wide
+    trace_.mark(4);
     if (part == 0) {
         for (int i = tid; i < NSRC * HOP; i += 256) {
             const int ear = i / HOP, n = i % HOP;
@@ -1102,7 +1111,9 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
             }
         }
     }
+    trace_.mark(5);
     cluster.sync();                         // nobody leaves while CTA 0 may still read its shared memory
+    trace_.mark(6);
     // ordinary call: the last CTA to finish advances the header (a pipelined graph runs several back_kernels
     // at once and advances it with advance_header_kernel after all of its frames instead)
     if (frames_total == 1 && tid == 0) {

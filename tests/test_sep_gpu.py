@@ -250,10 +250,12 @@ def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
         y_pipe = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
         st_pipe = net._last_stream_state.to_reference()
         net.set_option("pipeline", 0)
+        net.set_option("fused_tail", 0)       # the sequential hops as the same separate kernels the pipeline runs
         y_seq = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
         st_seq = net._last_stream_state.to_reference()
     finally:
         net.set_option("pipeline", 1)
+        net.set_option("fused_tail", 1)
         net.reset_options()
     assert torch.equal(y_pipe, y_seq)
     assert torch.equal(st_pipe["gridnet_bufs"]["buf2"]["K_buf"], st_seq["gridnet_bufs"]["buf2"]["K_buf"])
@@ -264,7 +266,7 @@ def test_wavefront_pipeline_equals_sequential(model, dev, lanes):
 
 def test_launch_counter_counts_graph_nodes(model, dev):
     """bench.py's gpu_launches comes from l2h_sep_launch_count: a replayed CUDA graph counts its kernel nodes.  One
-    sequential hop = 1 front + 3 x 6 + 1 back = 20 kernels; a pipelined 8-hop stream = per hop front + back + 3 x (qkv, attention,
+    sequential hop = front1 + 3 x (BiLSTM, tail_kernel) + back = 8 kernels (20 as separate kernels: 1 + 3 x 6 + 1); a pipelined 8-hop stream = per hop front + back + 3 x (qkv, attention,
     attn_out), per block and 4-hop batch ONE launch each of W_ih GEMM, BiLSTM, mid_a, mid_b, mid_c, + the header advance + the
     clip-base kernel = 120 (15 kernels per hop; the per-hop stage A and mid_c of round 1 made it 23.75)."""
     import ctypes
@@ -279,6 +281,13 @@ def test_launch_counter_counts_graph_nodes(model, dev):
     _cabi.check(L.l2h_sep_launch_count(net._engine(), None, 1))
     net.predict(xd[..., :192], e, st, pad=False)
     _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
+    assert n.value == 8
+    net.set_option("fused_tail", 0)
+    try:
+        net.predict(xd[..., 128:320], e, st, pad=False)
+        _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
+    finally:
+        net.set_option("fused_tail", 1)
     assert n.value == 20
     st = net.init_buffers(1, dev)
     _cabi.check(L.l2h_sep_launch_count(net._engine(), None, 1))
@@ -287,6 +296,40 @@ def test_launch_counter_counts_graph_nodes(model, dev):
     _cabi.check(L.l2h_sep_launch_count(net._engine(), ctypes.byref(n), 1))
     # per hop: front, back, 3 x (qkv, attention, attn_out); per 4-hop batch and block: W_ih GEMM, BiLSTM, mid_a, mid_b, mid_c
     assert n.value == 8 * 11 + 2 * 3 * 5 + 1 + 1
+
+
+def test_one_hop_cluster_kernel_equals_separate_kernels(model, dev):
+    """The latency path (one-hop calls of a few streams) runs everything of a block after the BiLSTM as ONE 16-CTA cluster
+    kernel (hop_kernels.cuh: tail_kernel), which also projects the next block's BiLSTM input.  Same arithmetic per element,
+    but the LayerNorm statistics are combined from per-tile partials, so not bit-identical: 1e-5 against the separate
+    kernels for the output and the carried state over 70 hops (the K/V ring wraps), 1e-3 against the oracle."""
+    net, sd = model
+    T, B = 70, 2
+    x, _ = synth.mixture(B, 128 * T, seed0=291)
+    e = synth.embedding(B, seed0=292)
+    xd, ed = x.to(dev), e[:, 0].to(dev)
+    net.set_option("pipeline", 0)
+    try:
+        y_fused = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+        st_fused = net._last_stream_state.to_reference()
+        net.set_option("fused_tail", 0)
+        y_sep = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
+        st_sep = net._last_stream_state.to_reference()
+    finally:
+        net.set_option("fused_tail", 1)
+        net.set_option("pipeline", 1)
+    assert rs.rel_l2(y_fused, y_sep) < 1e-5
+    for i in range(3):
+        for k in ("K_buf", "V_buf", "h0", "c0"):
+            a, b = st_fused["gridnet_bufs"][f"buf{i}"][k], st_sep["gridnet_bufs"][f"buf{i}"][k]
+            assert rs.rel_l2(a, b) < 1e-5, (i, k)
+    _check(y_fused[:1], rs.sep_forward(sd, x[:1], e[:1]))
+    # the reference-shaped API takes the same path: predict() hop by hop
+    st = net.init_buffers(B, dev)
+    xp = F.pad(xd, (0, 64))
+    with torch.no_grad():
+        y_pred = torch.cat([net.predict(xp[..., 128 * i:128 * i + 192], ed, st, pad=False)[0] for i in range(12)], -1).cpu()
+    assert rs.rel_l2(y_pred, y_fused[..., :128 * 12]) < 1e-6
 
 
 def test_fold_mid_c_option(model, dev):
@@ -301,7 +344,7 @@ def test_fold_mid_c_option(model, dev):
     xd, ed = x.to(dev), e[:, 0].to(dev)
     y_def = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
     try:
-        net.set_option("fold_mid_c", 1)
+        net.set_option("fold_mid_c", 1)             # (also keeps the one-hop chain on its separate kernels)
         y_pipe = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
         net.set_option("pipeline", 0)
         y_seq = net.stream_dev(xd, ed, chunks_per_call=1).cpu()
