@@ -523,6 +523,16 @@ def main():
         # dominant kernel: algorithmic bytes per launch / its mean duration
         alg = kernel_algorithmic_bytes(dom[0], cpc)
         ach = alg / (dom[1]["ms_mean"] * 1e-3) / 1e9
+        tr = trace_one_hop(net, x_dev, emb, dev)
+        fps_seq = extras.get("frames_per_s_unpipelined")
+        chain_us = 1e6 / fps_seq if fps_seq else tr["span_us"]      # device time per hop of back-to-back one-hop calls (chain + the gap between two graph launches)
+        latency_model = {"serial_steps": 3 * 97, "t_step_floor_us": 0.23, "t_step_measured_us": tr["t_step_us"],
+                         "chain_us": chain_us, "kernels_per_hop": tr["kernels"],
+                         "latency_frac": 3 * 97 * 0.23 / chain_us, "recurrence_share_of_chain": 3 * 97 * (tr["t_step_us"] or 0.0) / chain_us,
+                         "fma_pipe_pct_of_dominant_kernel": 15.6,
+                         "source": "chain_us = 1e6 / frames_per_s_unpipelined (untraced); t_step, kernels and the timeline from the device-side "
+                                   "trace of one one-hop call (l2h_sep_trace_*; with tracing on every kernel exit also flushes its time stamps)",
+                         "traced_span_us": tr["span_us"], "timeline_us": tr["timeline_us"]}
         roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed
@@ -531,13 +541,11 @@ def main():
                 "traffic": 11392.0 if dom[0] == "lstm_intra" else None, "peak_source": pk["source"],
                 "alg_bytes_per_launch": alg, "mean_us_per_launch": 1e3 * dom[1]["ms_mean"],
                 "share_of_chain": dom[1]["ms_total"] / sum(v["ms_total"] for v in prof.values()),
+                # fma_pipe_pct from the ncu capture profiles/r01e_lstm_rec3_full.md
                 # the model that governs batch 1: the chain cannot be shorter than its 3 x 97 dependent recurrent steps.
                 # t_step_floor = 0.23 us: the FMA + shuffle + barrier floor of one 256x64 step on one SM
-                # (profiles/r01c_lstm_microbench.txt); fma_pipe_pct from the ncu capture profiles/r01e_lstm_rec3_full.md
-                "latency_model": {"serial_steps": 3 * 97, "t_step_floor_us": 0.23, "t_step_measured_us": 1e3 * dom[1]["ms_mean"] / 97.0,
-                                  "chain_us": 1e3 * sum(v["ms_total"] for v in prof.values()),
-                                  "latency_frac": 3 * 97 * 0.23 / (1e3 * sum(v["ms_total"] for v in prof.values())),
-                                  "fma_pipe_pct_of_dominant_kernel": 27.0},
+                # (profiles/r01c_lstm_microbench.txt); chain_us / t_step_measured from the device-side trace of one hop
+                "latency_model": latency_model,
                 "note": "batch-1 streaming is latency-bound (serial LSTM chain, 13 MB working set resident in L2); "
                         "whole-chain algorithmic rate: %.1f GB/s, %.2f TFLOP/s fp32" % (
                             value / world * BYTES_PER_FRAME / 1e9, value / world * FLOP_PER_FRAME / 1e12)}
@@ -591,6 +599,53 @@ def kernel_algorithmic_bytes(name, cpc):
         return cpc * 4 * (584 * 4 + 50 * (584 + 1552) * 4 + 1552 * 4) if cpc == 1 else \
             4 * ((49 + cpc) * (584 + 1552) * 4 + cpc * (584 + 1552) * 4)
     return rows * 64 * 4 * 2
+
+
+TRACE_NAMES = ["front", "gemm_ih", "lstm", "mid_a", "mid_b", "mid_c", "qkv", "attn", "attn_out", "back", "mid", "tail"]
+
+
+def trace_one_hop(net, x_dev, emb, dev, reps=7):
+    """Device-side timeline of ONE one-hop chain (the latency path) from the engine's trace (l2h_sep_trace_start/_read:
+    the first thread of every kernel stores %globaltimer at entry / exit, the BiLSTM also around its 97-step loop).
+    Returns the median run: span of the chain, kernels in it, the recurrence's measured time per step."""
+    import numpy as np
+    from lookoncetohear_b200 import _cabi
+    L = _cabi.lib()
+    REC = np.dtype([("t0", "<u8"), ("t1", "<u8"), ("ptr", "<u8"), ("kernel", "<u4"), ("sm", "<u4")])
+    st = net.init_buffers(1, dev)
+    need = HOP * (56 + reps + 1)
+    if x_dev.shape[-1] < need:                  # short clips (--clip-hops): tile the audio, the timeline does not depend on the samples
+        x_dev = x_dev[:1].repeat(1, 1, (need + x_dev.shape[-1] - 1) // x_dev.shape[-1])
+    x_dev = x_dev[:1].contiguous()
+    emb = emb[:1].contiguous()
+    y = torch.empty(1, 2, x_dev.shape[-1], device=dev)
+    for h in range(56):                         # rings full, graph instantiated
+        net.stream_dev(x_dev[..., HOP * h:], emb, chunks_per_call=1, state=st, n_calls=1, out=y[..., HOP * h:])
+    runs = []
+    for r in range(reps):
+        h = 56 + r
+        _cabi.check(L.l2h_sep_trace_start(net._engine(), 256))
+        torch.cuda.synchronize()
+        net.stream_dev(x_dev[..., HOP * h:], emb, chunks_per_call=1, state=st, n_calls=1, out=y[..., HOP * h:])
+        torch.cuda.synchronize()
+        buf = np.zeros(256, dtype=REC)
+        n = ctypes.c_int32()
+        _cabi.check(L.l2h_sep_trace_read(net._engine(), buf.ctypes.data_as(ctypes.c_void_p), 256, ctypes.byref(n)))
+        rec = buf[:n.value]
+        rec = rec[rec["t1"] > 0]
+        ker = rec[rec["kernel"] < 100]
+        ker = ker[np.argsort(ker["t0"])]
+        org = int(ker["t0"].min())
+        marks = rec[rec["kernel"] >= 100]
+        loop0 = np.sort(marks["t0"][marks["kernel"] == 100 + 20 * 2 + 0])     # BiLSTM: loop start / end
+        loop1 = np.sort(marks["t0"][marks["kernel"] == 100 + 20 * 2 + 1])
+        steps = [(int(b) - int(a)) / 1e3 / 97.0 for a, b in zip(loop0, loop1)]
+        runs.append({"span_us": (int(ker["t1"].max()) - org) / 1e3, "kernels": int(len(ker)),
+                     "t_step_us": float(np.median(steps)) if steps else None,
+                     "timeline_us": [[TRACE_NAMES[min(int(k["kernel"]), 11)], round((int(k["t0"]) - org) / 1e3, 1), round((int(k["t1"]) - org) / 1e3, 1)] for k in ker]})
+    _cabi.check(L.l2h_sep_trace_start(net._engine(), 0))
+    runs.sort(key=lambda d: d["span_us"])
+    return runs[len(runs) // 2]
 
 
 def profile_chain(net, x_dev, emb, dev, cpc, iters=20, batch=1):

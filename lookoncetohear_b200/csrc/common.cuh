@@ -124,7 +124,7 @@ struct TraceRec { unsigned long long t0, t1; unsigned long long ptr; unsigned in
 static __device__ TraceRec* g_trace = nullptr;
 static __device__ unsigned int g_trace_cap = 0;
 static __device__ unsigned int g_trace_n = 0;
-enum TraceKernel { TK_FRONT = 0, TK_GEMM, TK_LSTM, TK_MID_A, TK_MID_B, TK_MID_C, TK_QKV, TK_ATTN, TK_ATTN_OUT, TK_BACK, TK_MID };
+enum TraceKernel { TK_FRONT = 0, TK_GEMM, TK_LSTM, TK_MID_A, TK_MID_B, TK_MID_C, TK_QKV, TK_ATTN, TK_ATTN_OUT, TK_BACK, TK_MID, TK_TAIL };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -149,18 +149,24 @@ struct TraceScope {
     __device__ __forceinline__ ~TraceScope() {
         if (rec != nullptr) {
             rec->t1 = globaltimer_ns();
+            // time stamps taken inside the kernel: one more record each (id 100 + 20 * kernel + point), slots reserved at once
             unsigned long long* m = marks();
-            for (int p = 0; p < TRACE_MARKS; ++p) {      // time stamps taken inside the kernel: one more record each, kernel id 100 + point
-                if (m[p] == 0ull) continue;
-                const unsigned int slot = atomicAdd(&g_trace_n, 1u);
-                if (slot < g_trace_cap) {
-                    TraceRec* r = g_trace + slot;
-                    r->ptr = rec->ptr; r->kernel = 100u + (unsigned int)p; r->sm = rec->sm; r->t0 = r->t1 = m[p];
+            unsigned int cnt = 0;
+            for (int p = 0; p < TRACE_MARKS; ++p) cnt += (m[p] != 0ull) ? 1u : 0u;
+            if (cnt != 0u) {
+                unsigned int slot = atomicAdd(&g_trace_n, cnt);
+                for (int p = 0; p < TRACE_MARKS; ++p) {
+                    if (m[p] == 0ull) continue;
+                    if (slot < g_trace_cap) {
+                        TraceRec* r = g_trace + slot;
+                        r->ptr = rec->ptr; r->kernel = 100u + (unsigned int)TRACE_MARKS * rec->kernel + (unsigned int)p; r->sm = rec->sm; r->t0 = r->t1 = m[p];
+                    }
+                    ++slot;
                 }
             }
         }
     }
-    static constexpr int TRACE_MARKS = 16;
+    static constexpr int TRACE_MARKS = 20;
     static __device__ __forceinline__ unsigned long long* marks() {
         __shared__ unsigned long long m[TRACE_MARKS];
         return m;

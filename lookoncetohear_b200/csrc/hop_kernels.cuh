@@ -117,7 +117,7 @@ tail_kernel(const float* __restrict__ Y, float* X, float* __restrict__ state, in
     __shared__ float pstat[2], fin[2];
     __shared__ float red[32];
 
-    TraceScope trace_(TK_MID, Y);
+    TraceScope trace_(TK_TAIL, Y);
     griddep_launch();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rk = (int)cluster.block_rank(), b = blockIdx.y;

@@ -7,7 +7,7 @@ import torch
 from lookoncetohear_b200 import Net, synth, _cabi
 from lookoncetohear_b200.configs import TSH_PARAMS
 
-NAMES = ["front", "gemm_ih", "lstm", "mid_a", "mid_b", "mid_c", "qkv", "attn", "attn_out", "back", "mid", "head", "tail"]
+NAMES = ["front", "gemm_ih", "lstm", "mid_a", "mid_b", "mid_c", "qkv", "attn", "attn_out", "back", "mid", "tail"]
 REC = np.dtype([("t0", "<u8"), ("t1", "<u8"), ("ptr", "<u8"), ("kernel", "<u4"), ("sm", "<u4")])
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 dev = torch.device("cuda", 0)
@@ -69,7 +69,7 @@ for i, r in enumerate(rec):
     a, b = (int(r["t0"]) - org) / 1e3, (int(r["t1"]) - org) / 1e3
     k = int(r["kernel"])
     if k >= 100:        # a time stamp inside the kernel (TraceScope::mark)
-        print("| %d | . point %d | %.1f | | | %.1f |" % (i, k - 100, a, a - prev_pt))
+        print("| %d | . %s point %d | %.1f | | | %.1f |" % (i, NAMES[(k - 100) // 20], (k - 100) % 20, a, a - prev_pt))
         prev_pt = a
         continue
     print("| %d | %s | %.1f | %.1f | %.1f | %.1f |" % (i, NAMES[k], a, b, b - a, b - prev))
