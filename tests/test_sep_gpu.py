@@ -332,6 +332,23 @@ def test_one_hop_cluster_kernel_equals_separate_kernels(model, dev):
     assert rs.rel_l2(y_pred, y_fused[..., :128 * 12]) < 1e-6
 
 
+def test_one_hop_form_switches_with_the_number_of_streams(model, dev):
+    """A one-hop call takes the cluster-kernel form only while all its 16-CTA clusters fit on the device at once (7 on a
+    B200); a call with more streams runs the separate kernels.  The same stream must come out the same (1e-5) from a
+    4-stream call (cluster form) and from a 12-stream call (separate kernels), state carried over 8 hops."""
+    net, _ = model
+    B, T = 12, 8
+    x, _ = synth.mixture(B, 128 * T, seed0=391)
+    e = synth.embedding(B, seed0=392)
+    xp = F.pad(x, (0, 64)).to(dev)
+    ed = e[:, 0].to(dev)
+    st_all, st_few = net.init_buffers(B, dev), net.init_buffers(4, dev)
+    with torch.no_grad():
+        y_all = torch.cat([net.predict(xp[..., 128 * i:128 * i + 192], ed, st_all, pad=False)[0] for i in range(T)], -1).cpu()
+        y_few = torch.cat([net.predict(xp[:4, :, 128 * i:128 * i + 192], ed[:4], st_few, pad=False)[0] for i in range(T)], -1).cpu()
+    assert rs.rel_l2(y_all[:4], y_few) < 1e-5
+
+
 def test_fold_mid_c_option(model, dev):
     """Engine option "fold_mid_c": the inter Linear runs inside the serial mid kernel and the Q/K/V projection inside
     qkv_kernel (three kernels fewer per hop).  A different kernel split, so not bit-identical to the default -- the
