@@ -362,10 +362,13 @@ inline cudaError_t launch_rows_gemm_cfg(const GemmArgs& g, cudaStream_t st, bool
 
 // Pick a tile by problem size: small M (one streaming frame = 97 rows) wants many small CTAs,
 // large M wants the 64x128 tile.  N must be a multiple of 64; K a multiple of 64.
-inline cudaError_t launch_rows_gemm(const GemmArgs& g, cudaStream_t st, bool pdl = false) {
+// `shape`: 0 = by size (below); 1 = 64x64 tiles, 2 = the persistent 128-row form, whatever M is (the pipelined graph's 4-hop
+// batches of 388 rows: fewer, fatter CTAs compete less with the other stages' kernels)
+inline cudaError_t launch_rows_gemm(const GemmArgs& g, cudaStream_t st, bool pdl = false, int shape = 0) {
     if (g.N % 64 != 0 || g.K % 64 != 0 || g.M <= 0) return cudaErrorInvalidValue;
     if (g.ln_g && g.K != 64) return cudaErrorInvalidValue;
-    if (g.M <= 2048) return launch_rows_gemm_cfg<16, 64, 2, 4>(g, st, pdl);     // 128 threads
+    if (shape == 1) return launch_rows_gemm_cfg<64, 64, 4, 4>(g, st, pdl);
+    if (g.M <= 2048 && shape == 0) return launch_rows_gemm_cfg<16, 64, 2, 4>(g, st, pdl);     // 128 threads
     {   // large M: persistent kernel with the weight slab resident in shared memory (when it fits)
         const int bn = (g.N % 128 == 0) ? 128 : 64;
         const size_t smem = ((size_t)g.K * bn + (size_t)GK * 132) * sizeof(float);

@@ -88,6 +88,7 @@ struct SepEngine {
     int64_t pipe_budget = 0; // bytes the pipelined workspace may take (min(24 GB, half of the free memory at first use))
     int pipe_frames = 0;     // one-hop chains per pipelined graph (<= PIPE_MAX_FRAMES); 0 = auto: as many as a 24 GB workspace holds
     int pipe_alanes = 12;    // BiLSTM (stage A) hops in flight per block (<= PIPE_LANES)
+    int pipe_gemm_shape = 0; // tile shape of the pipelined W_ih GEMM (gemm.cuh: launch_rows_gemm), option "pipeline_gemm_shape"
     int pipe_midb_hops = 4;       // pipeline: consecutive hops one mid_b launch takes (<= PIPE_MIDB_MAX)
     int pipe_skip = 0;            // DEBUG (timing experiments only): bit mask of pipeline stages NOT to launch
     int pipe_pdl = 16;            // pipeline: stages launched with programmatic dependent launch (bit mask; 16 = mid_b)
@@ -799,7 +800,7 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                 g.A = X; g.lda = 64; g.a_rows_per_seq = rows; g.a_seq_stride = slot;
                 g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512; g.c_rows_per_seq = rows; g.c_seq_stride = slot;
                 g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = rows * nh; g.N = 512; g.K = 64;
-                if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0));
+                if (!(e->pipe_skip & 2)) CK(launch_rows_gemm(g, st_a, (ppdl & 2) != 0, e->pipe_gemm_shape));
                 LstmArgs l{};
                 l.gx = GX; l.gx_ld = 512; l.out = Y; l.out_ld = 128; l.whh = W.whh1;
                 l.nseq = B * nh; l.L = NF; l.inner_count = B; l.outer_stride = slot / 512; l.inner_stride = NF; l.step_stride = 1;
@@ -1362,6 +1363,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "pipeline_lanes") e->pipe_alanes = std::max(1, std::min(PIPE_LANES, (int)value));
     else if (n == "pipeline_debug_skip") e->pipe_skip = value;
     else if (n == "pipeline_pdl") e->pipe_pdl = value;
+    else if (n == "pipeline_gemm_shape") e->pipe_gemm_shape = std::max(0, std::min(2, (int)value));
     else if (n == "pipeline_midb_hops") e->pipe_midb_hops = std::max(1, std::min(PIPE_MIDB_MAX, (int)value));
     else if (n == "pipeline_split_mid") e->pipe_split_mid = value != 0;
     else if (n == "pipeline_qkv_lanes") e->pipe_qlanes = std::max(1, std::min(PIPE_QLANES, (int)value));

@@ -300,7 +300,11 @@ class Net(nn.Module):
                                "hand-written CUDA with no CPU fallback")
 
     # ---- reference API ---------------------------------------------------------------------
-    def init_buffers(self, batch_size, device):
+    def init_buffers(self, batch_size, device, out=None):
+        """Fresh streaming state for `batch_size` streams (net.py:40-41 of the reference).  `out`: a SepState of the same batch
+        size to re-initialise IN PLACE -- the engine's cached CUDA graphs are keyed on the state's address, so a service that
+        resets a stream keeps its graphs warm this way (a new allocation means one more capture + instantiation of the
+        clip-sized pipelined graph, ~0.1-0.4 s)."""
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("lookoncetohear_b200.Net.init_buffers: CUDA device required (no CPU fallback)")
@@ -310,7 +314,9 @@ class Net(nn.Module):
         n = ctypes.c_size_t()
         _cabi.check(L.l2h_sep_state_bytes(h, batch_size, ctypes.byref(n)))
         hb, stride, offs = self._state_layout()
-        buf = torch.empty(n.value // 4, dtype=torch.float32, device=device)
+        if out is not None and (out.batch != batch_size or out.buf.device != device or out.buf.numel() != n.value // 4):
+            raise ValueError("init_buffers(out=...): the state to reuse has another batch size, device or layout")
+        buf = out.buf if out is not None else torch.empty(n.value // 4, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             _cabi.check(L.l2h_sep_state_init(h, buf.data_ptr(), batch_size,
                                              torch.cuda.current_stream(device).cuda_stream))

@@ -349,6 +349,24 @@ def test_one_hop_form_switches_with_the_number_of_streams(model, dev):
     assert rs.rel_l2(y_all[:4], y_few) < 1e-5
 
 
+def test_init_buffers_in_place(model, dev):
+    """init_buffers(out=state) re-initialises a state at its address (the engine's graphs are keyed on it): same pointer,
+    header back to zero, and the stream that follows equals one on a new state."""
+    net, _ = model
+    x, _ = synth.mixture(1, 128 * 6, seed0=491)
+    e = synth.embedding(1, seed0=492)[:, 0].to(dev)
+    xd = x.to(dev)
+    st = net.init_buffers(1, dev)
+    y0 = net.stream_dev(xd, e, chunks_per_call=1, state=st).cpu()
+    assert st.header()[0] == 6
+    st2 = net.init_buffers(1, dev, out=st)
+    assert st2.buf.data_ptr() == st.buf.data_ptr() and st2.header() == (0, 0)
+    y1 = net.stream_dev(xd, e, chunks_per_call=1, state=st2).cpu()
+    assert torch.equal(y0, y1)
+    with pytest.raises(ValueError):
+        net.init_buffers(2, dev, out=st)
+
+
 def test_fold_mid_c_option(model, dev):
     """Engine option "fold_mid_c": the inter Linear runs inside the serial mid kernel and the Q/K/V projection inside
     qkv_kernel (three kernels fewer per hop).  A different kernel split, so not bit-identical to the default -- the
