@@ -208,7 +208,7 @@ template <int NSEQ>
 __global__ void __launch_bounds__(128, 2)
 lstm_rec4_kernel(const LstmArgs a) {
     __shared__ __align__(16) float hbuf[2][NSEQ][64];
-    __shared__ __align__(16) float gring[L3_STAGES][NSEQ][256];
+    extern __shared__ __align__(16) float gring[];          // [L3_STAGES][NSEQ][256]
 
     griddep_launch();
     const int tid = threadIdx.x;
@@ -262,7 +262,7 @@ lstm_rec4_kernel(const LstmArgs a) {
                 const int idx = tid + 128 * u, r = idx >> 6, chunk = idx & 63;
                 const int it = 4 * g + r;
                 if (valid[s] && it < a.L)
-                    cp_async16(&gring[(g % 2) * 4 + r][s][chunk * 4], grow[s] + (int64_t)it * g_step + chunk * 4);
+                    cp_async16(&gring[(((g % 2) * 4 + r) * NSEQ + s) * 256 + chunk * 4], grow[s] + (int64_t)it * g_step + chunk * 4);
             }
         }
         cp_async_commit();
@@ -282,7 +282,7 @@ lstm_rec4_kernel(const LstmArgs a) {
         float2 g2[NSEQ];
 #pragma unroll
         for (int s = 0; s < NSEQ; ++s) {
-            g2[s] = *reinterpret_cast<const float2*>(&gring[it % L3_STAGES][s][j * 4 + 2 * kh]);
+            g2[s] = *reinterpret_cast<const float2*>(&gring[((it % L3_STAGES) * NSEQ + s) * 256 + j * 4 + 2 * kh]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[s][q] = make_float2(0.f, 0.f);
         }
@@ -367,6 +367,8 @@ lstm_rec4_kernel(const LstmArgs a) {
     }
 }
 
+constexpr size_t lstm_rec4_smem(int nseq) { return (size_t)L3_STAGES * nseq * 256 * sizeof(float); }
+
 inline cudaError_t configure_lstm() {
     cudaError_t e = cudaFuncSetAttribute(lstm_rec3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
@@ -377,11 +379,13 @@ inline cudaError_t launch_lstm_rec(const LstmArgs& a, cudaStream_t st, bool pdl 
     const int ctas1 = a.nseq * a.ndir;
     if (ctas1 <= 148 && (size_t)a.L * 1024 <= 200 * 1024)      // latency mode: one sequence per CTA, preloaded
         return launch_k(pdl, lstm_rec3_kernel<1, true>, dim3(a.nseq, a.ndir), dim3(128), (size_t)a.L * 1024, st, a);
+    // many sequences: NSEQ per CTA in lock-step (stage by stage), at most 4.  (Six per CTA, to fit 1 552 sequences in ONE wave of
+    // 259 CTAs instead of 388 CTAs in two, was measured: 6.9 us per step against 2 x 2.7 -- slower, 226 registers; not kept.)
     int per = 1;
     while (per < 4 && ((a.nseq + per - 1) / per) * a.ndir > 296) per *= 2;
     dim3 grid((a.nseq + per - 1) / per, a.ndir);
-    if (per == 2) return launch_k(pdl, lstm_rec4_kernel<2>, grid, dim3(128), 0, st, a);   // many sequences: stage by stage
-    if (per == 4) return launch_k(pdl, lstm_rec4_kernel<4>, grid, dim3(128), 0, st, a);
+    if (per == 2) return launch_k(pdl, lstm_rec4_kernel<2>, grid, dim3(128), lstm_rec4_smem(2), st, a);   // many sequences: stage by stage
+    if (per == 4) return launch_k(pdl, lstm_rec4_kernel<4>, grid, dim3(128), lstm_rec4_smem(4), st, a);
     return launch_k(pdl, lstm_rec3_kernel<1, false>, grid, dim3(128), 0, st, a);
 }
 

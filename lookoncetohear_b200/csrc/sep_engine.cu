@@ -103,6 +103,7 @@ struct SepEngine {
     bool fold_mid_c = false;      // no mid_c / no projection in the mid kernels: Linear in mid_b2, Q/K/V projection in qkv (untested)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
+    bool use_back_many = true;   // calls of several frames: back_many_kernel (one cluster per chunk of frames) instead of one cluster per frame (option "back_many")
     bool use_tail = true;    // one-hop calls of a few streams: mid + qkv + attention + attn_out (+ next W_ih) as ONE 16-CTA cluster kernel (option "fused_tail")
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
 };
@@ -332,6 +333,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(qkv_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QKV_MANY_SMEM));
     CK(cudaFuncSetAttribute(attn_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AOUT_SMEM));
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
+    CK(cudaFuncSetAttribute(back_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_MANY_SMEM));
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(cudaFuncSetAttribute(mid_noproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
@@ -654,8 +656,18 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
-    CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL * T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
-                a.pos_rel, 0, 1, 0, (int64_t)0));
+    if (T > 1 && e->use_back_many) {
+        // many frames: one cluster walks a contiguous chunk of a stream's frames (filters loaded once, rows staged once);
+        // as many clusters as stay resident together (3 CTAs of 72 KB per SM)
+        const int per_stream = std::max(1, (148 * 3 / BACK_CL) / B);
+        const int chunk = (T + per_stream - 1) / per_stream;
+        const int n_chunks = (T + chunk - 1) / chunk;
+        CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_many_kernel, dim3(BACK_CL * n_chunks, B), dim3(256), BACK_MANY_SMEM, st, (const float*)X, y, ybs,
+                          ycs, y_len, state, ss, e->w, T, a.pos_rel, chunk));
+    } else {
+        CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL * T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
+                    a.pos_rel, 0, 1, 0, (int64_t)0));
+    }
     MARK("back");
 #undef MARK
     return 0;
@@ -1375,6 +1387,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "pdl") e->use_pdl = value != 0;
     else if (n == "fused_mid") e->use_mid = value != 0;
     else if (n == "fused_tail") e->use_tail = value != 0;
+    else if (n == "back_many") e->use_back_many = value != 0;
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else if (n == "tensor_cores") e->use_tc = value != 0;

@@ -168,15 +168,23 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
 #pragma unroll
         for (int k = 0; k < 36; ++k) wr[k] = __ldg(w.wc + o * 36 + k);
         const float bias = __ldg(w.bc + o);
-        for (int f = fg; f < NF; f += 4) {
-            float acc = bias;
+        // four rows at a time: four independent 36-long FMA chains per thread instead of one (the single chain made the conv
+        // 6 us of a frame's 11: profiles/r02k_one_hop_latency_path.md); per output the same order of additions as before
+        for (int f = fg; f < NF; f += 16) {
+            float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) acc = fmaf(wr[c * 9 + i * 3 + j], U[i][c][f + j], acc);
-            X[(((int64_t)b * T + t) * NF + f) * CH + o] = acc;
+                    for (int j = 0; j < 3; ++j) {
+                        const float wv = wr[c * 9 + i * 3 + j];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[u] = fmaf(wv, U[i][c][min(f + 4 * u, NF - 1) + j], acc[u]);
+                    }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f + 4 * u < NF) X[(((int64_t)b * T + t) * NF + f + 4 * u) * CH + o] = acc[u];
         }
     }
     trace_.mark(3);
@@ -1128,6 +1136,182 @@ back_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstrid
     }
 }
 
+
+// K5 for calls of MANY frames (whole utterances, offline batches): the same arithmetic as back_kernel, frame by frame in the
+// same order (results are bit-identical), but one cluster walks a contiguous CHUNK of frames of a stream: its synthesis
+// filter slices (37 KB per CTA) are loaded once instead of once per frame, every frame's rows are staged once (4-slot ring,
+// the next frame's TMA in flight under the current frame's work) instead of four times, and the deconvolved spectrum of
+// frame t-1 is carried in shared memory instead of being recomputed -- back_kernel's one-cluster-per-frame form was 12 % of
+// the offline step (8 000 clusters of 4 CTAs per 16 x 500 frames, profiles/r02d_kernel_us_by_call_size.jsonl).
+// grid (BACK_CL * n_chunks, B) in clusters of BACK_CL, 256 threads; frames [c*chunk, min(T, (c+1)*chunk)) for cluster c.
+constexpr size_t BACK_MANY_SMEM = (size_t)(4 * (BACK_FMAX + 2) * 64 + 2 * BACK_FMAX * NFFT + 2 * NSRC * NROW + 2 * NSRC * NFFT) * sizeof(float);
+
+__global__ void __launch_bounds__(256)
+back_many_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride, int y_len,
+                 float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int chunk) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float sm[];
+    float* Xs = sm;                                    // ring [4: frame g -> slot (g + 4) & 3][nf + 2 rows: f0-1 .. f1][64]
+    float* Wf = Xs + 4 * (BACK_FMAX + 2) * 64;         // [2: re, im][nf][192] this CTA's synthesis filter rows
+    float* R = Wf + 2 * BACK_FMAX * NFFT;              // [2: frame g -> g & 1][2 ears][194]  (own bins only)
+    float* wacc = R + 2 * NSRC * NROW;                 // [2: frame g & 1][2 ears][192] partial synthesis sums
+    __shared__ __align__(8) unsigned long long fbar;   // filter
+    __shared__ __align__(8) unsigned long long xbar[4];// one per ring slot
+    const int part = (int)cluster.block_rank();
+    const int c = blockIdx.x / BACK_CL, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f0 = back_f0(part), f1 = back_f0(part + 1), nf = f1 - f0;
+    const int ld = nf + 2;
+    const int t0 = c * chunk, t1 = min(T, t0 + chunk);
+    griddep_launch();
+    if (tid == 0) {
+        mbar_init(&fbar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&xbar[i], 1);
+        mbar_fence_init();
+        mbar_expect_tx(&fbar, 2 * nf * NFFT * 4);
+        tma_load_1d(Wf, w.ws + (int64_t)f0 * NFFT, nf * NFFT * 4, &fbar);
+        tma_load_1d(Wf + nf * NFFT, w.ws + (int64_t)(NF + f0) * NFFT, nf * NFFT * 4, &fbar);
+    }
+    for (int i = tid; i < 4 * ld * 64; i += 256) {      // halo rows outside 0 .. 96 stay zero for the whole walk
+        const int f = f0 - 1 + (i / 64) % ld;
+        if (f < 0 || f >= NF) Xs[i] = 0.f;
+    }
+    float wr[2][36];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 36; ++k) wr[u][k] = __ldg(w.wd + (lane + 32 * u) * 36 + k);
+    float bd[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) bd[o] = __ldg(w.bd + o);
+    __syncthreads();
+    griddep_wait();
+    StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
+    const int par = (int)(hdr->ncalls & 1);
+    const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float* db = st + ST_DECONV + par * (2 * FC);
+    float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
+    const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
+    float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
+    const int lo = max(f0 - 1, 0), hi = min(f1 + 1, NF);          // staged bins that exist: [lo, hi)
+    // frame g of this call: g >= 0 from X, g = -1, -2 from the deconv tails the previous call left
+    auto stage = [&](int g) {                                     // thread 0
+        const int slot = (g + 4) & 3;
+        const float* src = (g < 0) ? db + (2 + g) * FC : X + ((int64_t)b * T + g) * FC;
+        fence_proxy_async();
+        mbar_expect_tx(&xbar[slot], (hi - lo) * 64 * 4);
+        tma_load_1d(Xs + (slot * ld + (lo - (f0 - 1))) * 64, src + lo * 64, (hi - lo) * 64 * 4, &xbar[slot]);
+    };
+    const int gfirst = max(t0 - 3, -2);                           // first frame this cluster stages
+    auto slot_parity = [&](int g) { return (unsigned)(((g - gfirst) >> 2) & 1); };      // a slot's barrier completes once per 4 frames
+    // deconv of the own bins for frame g (needs frames g, g-1, g-2 in the ring) -> R[g & 1]
+    auto deconv = [&](int g) {
+        float* Rg = R + (g & 1) * NSRC * NROW;
+        for (int f = f0 + warp; f < f1; f += 8) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float* xp = Xs + ((((g - i) + 4) & 3) * ld + (f + 2 - j - f0)) * 64;
+                    const float x0 = xp[lane], x1 = xp[lane + 32];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        acc[o] = fmaf(wr[0][o * 9 + i * 3 + j], x0, acc[o]);
+                        acc[o] = fmaf(wr[1][o * 9 + i * 3 + j], x1, acc[o]);
+                    }
+                }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const float v = warp_sum(acc[o]);
+                if (lane == 0) Rg[(o >> 1) * NROW + (o & 1) * NF + f] = v + bd[o];
+            }
+        }
+    };
+    if (t0 < t1) {
+        // prologue: frames t0-3 .. t0 into the ring (those that exist: >= -2), then the spectrum of frame t0-1
+        if (tid == 0)
+            for (int g = gfirst; g <= t0; ++g) stage(g);
+        for (int g = gfirst; g < t0; ++g) mbar_wait(&xbar[(g + 4) & 3], slot_parity(g));
+        if (t0 == 0) {                                 // the previous call's last spectrum (own bins)
+            for (int i = tid; i < NSRC * 2 * nf; i += 256) {
+                const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
+                R[NSRC * NROW + idx] = ib[idx];        // frame -1 -> slot (-1) & 1 = 1
+            }
+        } else {
+            deconv(t0 - 1);
+        }
+        mbar_wait(&fbar, 0);
+    }
+    for (int t = t0; t < t1; ++t) {
+        mbar_wait(&xbar[(t + 4) & 3], slot_parity(t));
+        __syncthreads();                               // frame t-1's readers of slot (t+1) & 3 = frame t-3's are done; R[(t-1)&1] complete
+        if (tid == 0 && t + 1 < t1) stage(t + 1);      // into the slot of frame t-3
+        deconv(t);
+        if (t == T - 1) {                              // next deconv tails: frames T-2, T-1 (own bins)
+            for (int i = tid; i < nf * 16; i += 256) {
+                const int r = i / 16, c4 = i % 16;
+                reinterpret_cast<float4*>(db_next + (f0 + r) * 64)[c4] =
+                    reinterpret_cast<const float4*>(Xs + ((((t - 1) + 4) & 3) * ld + 1 + r) * 64)[c4];
+                reinterpret_cast<float4*>(db_next + FC + (f0 + r) * 64)[c4] =
+                    reinterpret_cast<const float4*>(Xs + (((t + 4) & 3) * ld + 1 + r) * 64)[c4];
+            }
+        }
+        __syncthreads();                               // R[t & 1] (own bins) complete
+        float* wa = wacc + (t & 1) * NSRC * NFFT;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int item = tid + 256 * u;
+            if (item < NSRC * NFFT) {
+                const int ear = item / NFFT, n = item % NFFT;
+                const float* rr = R + ((((n < HOP) ? t : t - 1) & 1) * NSRC + ear) * NROW + f0;
+                float acc = 0.f;
+                for (int ri = 0; ri < 2; ++ri) {
+                    const float* wf = Wf + ri * nf * NFFT + n;
+                    const float* rv = rr + ri * NF;
+#pragma unroll 5
+                    for (int r = 0; r < nf; ++r) acc = fmaf(rv[r], wf[r * NFFT], acc);
+                }
+                wa[item] = acc;
+            }
+        }
+        if (t == T - 1)
+            for (int i = tid; i < NSRC * 2 * nf; i += 256) {
+                const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
+                ib_next[idx] = R[(t & 1) * NSRC * NROW + idx];
+            }
+        cluster.sync();                                // the four partial windows of frame t are complete and visible cluster-wide
+        if (part == 0) {                               // (wacc is double-buffered: the peers go on with frame t+1 meanwhile)
+            for (int i = tid; i < NSRC * HOP; i += 256) {
+                const int ear = i / HOP, n = i % HOP;
+                const int s = HOP * t + n + soff;
+                if (s < y_len) {
+                    float v = 0.f, tail = 0.f;
+#pragma unroll
+                    for (int p = 0; p < BACK_CL; ++p) {
+                        const float* pw = cluster.map_shared_rank(wa, p);
+                        v += pw[ear * NFFT + n];
+                        if (n < LOOKAHEAD) tail += pw[ear * NFFT + HOP + n];
+                    }
+                    if (n < LOOKAHEAD) v += tail;               // overlap-add of the previous frame's tail
+                    y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
+                }
+            }
+        }
+    }
+    cluster.sync();                         // nobody leaves while CTA 0 may still read its shared memory
+    if (tid == 0) {                         // the last CTA to finish advances the header
+        __threadfence();
+        const int prev = atomicAdd(&hdr->done, 1);
+        if (prev == (int)(gridDim.x * gridDim.y) - 1) {
+            hdr->pos += T;
+            hdr->ncalls += 1;
+            hdr->done = 0;
+            __threadfence();
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Tail of the attention output for calls with many rows, where the Linear(64->64) + PReLU ran as a tensor-core GEMM

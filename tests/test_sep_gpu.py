@@ -349,6 +349,34 @@ def test_one_hop_form_switches_with_the_number_of_streams(model, dev):
     assert rs.rel_l2(y_all[:4], y_few) < 1e-5
 
 
+def test_many_frame_back_kernel_is_bit_identical(model, dev):
+    """Calls of several frames finish in back_many_kernel (one cluster walks a chunk of a stream's frames: filters loaded
+    once, rows staged once, the previous frame's spectrum carried) instead of one back_kernel cluster per frame: the same
+    arithmetic in the same order, so outputs and the carried tails must be EQUAL -- whole clips, short calls (2, 3, 5 frames
+    per call, state threaded through, clip lengths that leave a ragged last call) and a batch."""
+    net, _ = model
+    x, _ = synth.mixture(3, 128 * 203, seed0=591)
+    e = synth.embedding(3, seed0=592)
+    xd, ed = x.to(dev), e.to(dev)
+
+    def run_all():
+        outs = [net(xd, ed).cpu(), net(xd[:1, :, :128 * 2], ed[:1]).cpu(), net(xd[:, :, :128 * 3 - 40], ed).cpu()]
+        for cpc in (2, 3, 5):
+            outs.append(net.stream_dev(xd[:, :, :128 * 41], ed[:, 0], chunks_per_call=cpc).cpu())
+            ref = net._last_stream_state.to_reference()
+            outs += [ref["deconv_buf"].cpu(), ref["istft_buf"].cpu()]
+        return outs
+
+    a = run_all()
+    net.set_option("back_many", 0)
+    try:
+        b = run_all()
+    finally:
+        net.set_option("back_many", 1)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
 def test_init_buffers_in_place(model, dev):
     """init_buffers(out=state) re-initialises a state at its address (the engine's graphs are keyed on it): same pointer,
     header back to zero, and the stream that follows equals one on a new state."""
