@@ -47,6 +47,11 @@ struct Slot {
     std::vector<float> raw;    // accumulate slots keep their tensor; the sum is formed at commit
 };
 
+// (sequence, direction) pairs from which the recurrence runs on the tensor cores (tc_lstm: 32 sequences per CTA, 9 472 per wave of
+// 296 CTAs at 16.8 us per step; CUDA cores: 4 per CTA, 1 184 per wave at 2.7 us).  Measured at the offline shape
+// (tools/offline_split_experiment.py): 3 492 inter sequences are faster as three CUDA-core waves than as 110 tensor-core CTAs.
+constexpr int TCL_MIN_SEQDIRS = 4096;
+
 struct SepEngine {
     l2h_sep_config cfg;
     int n_blocks;
@@ -103,6 +108,7 @@ struct SepEngine {
     bool fold_mid_c = false;      // no mid_c / no projection in the mid kernels: Linear in mid_b2, Q/K/V projection in qkv (untested)
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
+    int tcl_min_seqdirs = TCL_MIN_SEQDIRS;  // (sequence, direction) pairs from which the recurrence runs on the tensor cores (option "tc_lstm_min")
     bool use_back_many = true;   // calls of several frames: back_many_kernel (one cluster per chunk of frames) instead of one cluster per frame (option "back_many")
     bool use_tail = true;    // one-hop calls of a few streams: mid + qkv + attention + attn_out (+ next W_ih) as ONE 16-CTA cluster kernel (option "fused_tail")
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
@@ -378,15 +384,14 @@ static umma::BPlanes tc_planes(const SepEngine* e, int blk, int which, int ld) {
 }
 
 // the recurrence: tensor cores when there are enough sequences to fill the GPU with 32-sequence CTAs, else lstm.cuh
-constexpr int TCL_MIN_SEQDIRS = 2048;
 static cudaError_t lstm_any(SepEngine* e, const LstmArgs& l, cudaStream_t st, bool pdl) {
-    if (e->use_tc && (int64_t)l.nseq * l.ndir >= TCL_MIN_SEQDIRS) return launch_tc_lstm(l, e->tc_passes, st, pdl);
+    if (e->use_tc && (int64_t)l.nseq * l.ndir >= e->tcl_min_seqdirs) return launch_tc_lstm(l, e->tc_passes, st, pdl);
     return launch_lstm_rec(l, st, pdl);
 }
 
 // ... and with enough sequences the input projection moves into the recurrence kernel too (tc_lstm_x_kernel)
 static bool tc_fused_lstm(const SepEngine* e, const LstmArgs& l) {
-    return e->use_tc && e->fuse_ih && (int64_t)l.nseq * l.ndir >= TCL_MIN_SEQDIRS;
+    return e->use_tc && e->fuse_ih && (int64_t)l.nseq * l.ndir >= e->tcl_min_seqdirs;
 }
 
 // C[rows][N] = epi(LN?(A[rows][lda, first K]) W^T + bias) (+ R), plain row-major rows
@@ -1388,6 +1393,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "fused_mid") e->use_mid = value != 0;
     else if (n == "fused_tail") e->use_tail = value != 0;
     else if (n == "back_many") e->use_back_many = value != 0;
+    else if (n == "tc_lstm_min") e->tcl_min_seqdirs = std::max(1, (int)value);
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
     else if (n == "tensor_cores") e->use_tc = value != 0;

@@ -203,10 +203,10 @@ class Net(nn.Module):
         self._handle = None
         self._dirty = True                      # weights need (re)packing into the engine
         self._ws = None
-        # batch*frames per kernel chain.  18 clips of 500 frames: the intra recurrence (2 x 9 000 sequences, 32 per CTA) is then
-        # two FULL waves of the 296 resident CTAs; measured 629 k frames/s against 600 k at 16 clips, 587 k at 20
-        # (tools/offline_split_experiment.py)
-        self.max_frames_per_launch = 9216
+        # batch*frames per kernel chain.  36 clips of 500 frames: the intra recurrence (2 x 18 000 sequences, 32 per tensor-core CTA) is
+        # 3.8 waves of the 296 resident CTAs and the inter recurrence (3 492 sequences, 4 per CUDA-core CTA) 2.95 waves; measured
+        # 651 k frames/s against 628 k at 18 clips, 600 k at 16 (tools/offline_split_experiment.py)
+        self.max_frames_per_launch = 18432
 
     # ---- engine plumbing -------------------------------------------------------------------
     def _engine(self):

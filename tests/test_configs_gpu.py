@@ -172,10 +172,10 @@ def test_enrollment_batch_1024(embed_params, dev):
 
 def test_fused_input_projection_recurrence_option(sep, dev):
     """Engine option "fuse_ih": LayerNorm + W_ih + the recurrence as ONE tensor-core kernel (tc_lstm_x_kernel) for calls
-    with >= 2048 sequence-directions.  Off by default (measured slower than GEMM + tc_lstm, profiles/r02i); same gates."""
+    with >= 4096 sequence-directions.  Off by default (measured slower than GEMM + tc_lstm, profiles/r02i); same gates."""
     net, sd = sep
-    B = 10
-    x, tgt = synth.mixture(B, 128 * 110, seed0=2400)            # 10 x 110 frames: 2200 intra sequence-directions, 970 inter
+    B = 20
+    x, tgt = synth.mixture(B, 128 * 110, seed0=2400)            # 20 x 110 frames: 4400 intra sequence-directions, 1940 inter
     e = synth.embedding(B, seed0=2500)
     with torch.no_grad():
         y0 = net(x.to(dev), e.to(dev)).cpu()
@@ -185,5 +185,5 @@ def test_fused_input_projection_recurrence_option(sep, dev):
         finally:
             net.set_option("fuse_ih", 0)
     assert rs.rel_l2(y1, y0) < 1e-4
-    for b in (0, 9):
+    for b in (0, 19):
         assert rs.rel_l2(y1[b:b + 1], rs.sep_forward(sd, x[b:b + 1], e[b:b + 1])) <= 1e-3
