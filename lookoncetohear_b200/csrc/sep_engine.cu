@@ -109,7 +109,7 @@ struct SepEngine {
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
     int tcl_min_seqdirs = TCL_MIN_SEQDIRS;  // (sequence, direction) pairs from which the recurrence runs on the tensor cores (option "tc_lstm_min")
-    bool use_back_many = true;   // calls of several frames: back_many_kernel (one cluster per chunk of frames) instead of one cluster per frame (option "back_many")
+    bool use_back_many = true;   // calls of several frames: front_many_kernel / back_many_kernel (one CTA / cluster per chunk of frames) instead of one per frame (option "back_many")
     bool use_tail = true;    // one-hop calls of a few streams: mid + qkv + attention + attn_out (+ next W_ih) as ONE 16-CTA cluster kernel (option "fused_tail")
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
 };
@@ -341,6 +341,7 @@ static int set_attrs() {
     CK(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_SMEM));
     CK(cudaFuncSetAttribute(back_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BACK_MANY_SMEM));
     CK(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
+    CK(cudaFuncSetAttribute(front_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
     CK(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(cudaFuncSetAttribute(mid_noproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM));
     CK(cudaFuncSetAttribute(mid_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_B2_SMEM));
@@ -481,6 +482,12 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     if (fused_tail) {      // the frame as 13 row tiles: spectrum of the tile's bins, conv, and block 0's input projection
         CK(launch_k(false, front1_kernel, dim3(TAIL_TILES + 1, B), dim3(256), FRONT1_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w,
                     e->bw[0], GX, a.pos_rel, emb, PRE));
+    } else if (T > 1 && e->use_back_many) {      // many frames: one CTA walks a chunk of a stream's frames (one CTA per SM: 150 KB of filters)
+        const int per_stream = std::max(1, 148 / B);
+        const int chunk = (T + per_stream - 1) / per_stream;
+        const int n_chunks = (T + chunk - 1) / chunk;
+        CK(launch_k(false, front_many_kernel, dim3(n_chunks + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
+                    a.pos_rel, emb, PRE, chunk, n_chunks));
     } else {
         CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
                     a.pos_rel, emb, PRE, 0, 1, 0));

@@ -197,6 +197,125 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
     }
 }
 
+// K1 for calls of MANY frames: front_kernel's arithmetic frame by frame in the same order (bit-identical), but one CTA walks a
+// contiguous chunk of a stream's frames: the 150 KB of analysis filters are staged once per CTA instead of once per frame,
+// only the NEW frame's spectrum is computed (the two before it stay in a 3-slot ring; front_kernel recomputes them: 3x the STFT),
+// and the next frame's samples are fetched while the current frame is worked on.  grid (n_chunks + 1, B): the last CTA of a
+// stream is the speaker-gate memo.  Frames [c*chunk, min(T, (c+1)*chunk)) for CTA c.
+__global__ void __launch_bounds__(256)
+front_many_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len, float* __restrict__ X,
+                  float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, const float* __restrict__ emb,
+                  float* __restrict__ spk_pre, int chunk, int n_chunks) {
+    extern __shared__ __align__(16) float wat_s[];     // [192][196]
+    __shared__ __align__(16) float xs[NMIC][NFFT];      // the samples of the frame being transformed (>= 288 floats: gate CTA scratch)
+    __shared__ float U[3][4][100];      // ring: frame g -> slot (g + 3) % 3; [ch][1 + f], zero-padded in f
+    __shared__ __align__(8) unsigned long long wbar;
+    griddep_launch();
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (c == n_chunks) {               // the extra CTA of this stream: speaker-gate memo
+        griddep_wait();
+        spk_gate_cta(emb, spk_pre, state, sstride, w, b, &xs[0][0]);
+        return;
+    }
+    const int t0 = c * chunk, t1 = min(T, t0 + chunk);
+    if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) { mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM); tma_load_1d(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar); }
+    for (int i = tid; i < 3 * 4 * 100; i += 256) (&U[0][0][0])[i] = 0.f;
+    const int o = tid & 63, fg = tid >> 6;
+    float wr[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) wr[k] = __ldg(w.wc + o * 36 + k);
+    const float bias = __ldg(w.bc + o);
+    griddep_wait();
+    const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
+    const int par = (int)(hdr->ncalls & 1);
+    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+    const float* cb = st + ST_CONV + par * (2 * 4 * NF);
+    float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
+    const int sbase = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
+    const float* xb = x + (int64_t)b * x_bstride;
+    // samples of frame g: x[sbase + 128 g .. + 191] (zero outside the clip); thread tid fetches entries tid and tid + 256 of [2][192]
+    auto fetch = [&](int g, float& a0, float& a1) {
+        const int s0 = sbase + HOP * g;
+        { const int m = tid / NFFT, n = tid % NFFT, sidx = s0 + n; a0 = (sidx >= 0 && sidx < x_len) ? xb[(int64_t)m * x_cstride + sidx] : 0.f; }
+        a1 = 0.f;
+        if (tid + 256 < NMIC * NFFT) { const int i = tid + 256, m = i / NFFT, n = i % NFFT, sidx = s0 + n; a1 = (sidx >= 0 && sidx < x_len) ? xb[(int64_t)m * x_cstride + sidx] : 0.f; }
+    };
+    auto put = [&](float a0, float a1) {
+        (&xs[0][0])[tid] = a0;
+        if (tid + 256 < NMIC * NFFT) (&xs[0][0])[tid + 256] = a1;
+    };
+    // spectrum of the frame whose samples are in xs -> ring slot of frame g: channels [Re m0, Re m1, Im m0, Im m1]
+    auto stft = [&](int g) {
+        if (tid < NROW) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+            for (int n = 0; n < NFFT; ++n) {
+                const float wv = wat_s[n * 196 + tid];
+                a0 = fmaf(wv, xs[0][n], a0);
+                a1 = fmaf(wv, xs[1][n], a1);
+            }
+            const int ri = tid / NF, f = tid % NF, slot = (g + 3) % 3;
+            U[slot][ri * 2 + 0][1 + f] = a0;
+            U[slot][ri * 2 + 1][1 + f] = a1;
+        }
+    };
+    float n0, n1;
+    mbar_wait(&wbar, 0);
+    // the two frames before the chunk: from the tails of the previous call (g < 0) or recomputed
+    for (int g = t0 - 2; g < t0; ++g) {
+        __syncthreads();
+        if (g < 0) {
+            for (int e = tid; e < 4 * NF; e += 256) U[(g + 3) % 3][e / NF][1 + e % NF] = cb[(2 + g) * 4 * NF + e];
+        } else {
+            fetch(g, n0, n1);
+            put(n0, n1);
+            __syncthreads();
+            stft(g);
+        }
+    }
+    __syncthreads();
+    fetch(t0, n0, n1);
+    for (int t = t0; t < t1; ++t) {
+        put(n0, n1);
+        __syncthreads();                           // samples of frame t visible; frame t-1's conv (reads all three slots) is done
+        if (t + 1 < t1) fetch(t + 1, n0, n1);      // next frame's samples in flight under this frame's work
+        stft(t);
+        __syncthreads();
+        // conv: X[f][o] = b_o + sum_{c,i,j} Wc[o][c][i][j] * U[frame t-2+i][c][f-1+j]
+        {
+            const float (*U0)[100] = U[(t - 2 + 3) % 3];
+            const float (*U1)[100] = U[(t - 1 + 3) % 3];
+            const float (*U2)[100] = U[(t + 3) % 3];
+            for (int f = fg; f < NF; f += 16) {
+                float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float* ur = (i == 0) ? U0[cc] : (i == 1 ? U1[cc] : U2[cc]);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const float wv = wr[cc * 9 + i * 3 + j];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) acc[u] = fmaf(wv, ur[min(f + 4 * u, NF - 1) + j], acc[u]);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (f + 4 * u < NF) X[(((int64_t)b * T + t) * NF + f + 4 * u) * CH + o] = acc[u];
+            }
+        }
+        if (t == T - 1) {                          // next conv tails = spectrogram rows of the call's last two frames
+            for (int e = tid; e < 4 * NF; e += 256) {
+                cb_next[e] = U[(t - 1 + 3) % 3][e / NF][1 + e % NF];
+                cb_next[4 * NF + e] = U[(t + 3) % 3][e / NF][1 + e % NF];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K6 speaker gate: g = LN_6208(W e + b), stored (f, c)   (tfgridnet_causal.py:247-248).
 // The reference recomputes it on every call; it only changes when the embedding does, so it is

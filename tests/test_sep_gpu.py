@@ -349,9 +349,10 @@ def test_one_hop_form_switches_with_the_number_of_streams(model, dev):
     assert rs.rel_l2(y_all[:4], y_few) < 1e-5
 
 
-def test_many_frame_back_kernel_is_bit_identical(model, dev):
-    """Calls of several frames finish in back_many_kernel (one cluster walks a chunk of a stream's frames: filters loaded
-    once, rows staged once, the previous frame's spectrum carried) instead of one back_kernel cluster per frame: the same
+def test_many_frame_front_and_back_kernels_are_bit_identical(model, dev):
+    """Calls of several frames start in front_many_kernel and finish in back_many_kernel (one CTA / cluster walks a chunk of a
+    stream's frames: filters loaded once, rows staged once, the neighbouring frames' spectra carried) instead of one
+    front_kernel CTA and one back_kernel cluster per frame: the same
     arithmetic in the same order, so outputs and the carried tails must be EQUAL -- whole clips, short calls (2, 3, 5 frames
     per call, state threaded through, clip lengths that leave a ragged last call) and a batch."""
     net, _ = model
@@ -364,7 +365,7 @@ def test_many_frame_back_kernel_is_bit_identical(model, dev):
         for cpc in (2, 3, 5):
             outs.append(net.stream_dev(xd[:, :, :128 * 41], ed[:, 0], chunks_per_call=cpc).cpu())
             ref = net._last_stream_state.to_reference()
-            outs += [ref["deconv_buf"].cpu(), ref["istft_buf"].cpu()]
+            outs += [ref["conv_buf"].cpu(), ref["deconv_buf"].cpu(), ref["istft_buf"].cpu()]
         return outs
 
     a = run_all()
