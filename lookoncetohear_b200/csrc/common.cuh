@@ -7,8 +7,17 @@ namespace l2h {
 
 #define L2H_DEVINL __device__ __forceinline__
 
-// ---- packed fp32x2 FMA (Blackwell FFMA2): d.xy = a.xy * b.xy + c.xy -------------------------
+// ---- d.xy = a.xy * b.xy + c.xy ------------------------------------------------------------------------------------
+// L2H_FFMA2 = 1: the packed fma.rn.f32x2 (SASS FFMA2); 0: two scalar fma.rn.f32 (SASS FFMA) -- the same two roundings, bit-identical.
+// tools/ffma_microbench.cu on a B200 SM: FFMA 1.0 cycle per warp-instruction and scheduler with one operand shared between
+// neighbouring instructions (127 FMA/clk/SM), 1.2-2.3 with three distinct registers; FFMA2 2.35 (109 FMA/clk/SM) resp. 3.15 (81).  The
+// packed form is no faster per FMA -- it halves the instruction count, which is what the latency-shaped kernels here are short of:
+// built with scalar FFMAs the one-hop chain is 1 % faster, the many-sequence recurrences 7-9 % and the pipelined clip 5 % slower.
+#ifndef L2H_FFMA2
+#define L2H_FFMA2 1
+#endif
 L2H_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+#if L2H_FFMA2
     unsigned long long d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;"
         : "=l"(d)
@@ -16,6 +25,9 @@ L2H_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
           "l"(*reinterpret_cast<unsigned long long*>(&b)),
           "l"(*reinterpret_cast<unsigned long long*>(&c)));
     return *reinterpret_cast<float2*>(&d);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
 }
 
 L2H_DEVINL float warp_sum(float v) {
