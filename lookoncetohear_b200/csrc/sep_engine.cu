@@ -813,8 +813,14 @@ static int enqueue_pipeline(SepEngine* e, const ChainArgs& a, int K, cudaStream_
                         // x / y are the group's buffers; hop k works at sample offset k*128 (plus, with pos_rel, the clip
                         // position the device derives from the state header)
                         cudaStream_t sF = sFront(k);
-                        if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(2, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs,
+                        // the speaker-gate memo CTA (blockIdx.x == 1) rides with hop 0 only: one builder of ST_GATE per group
+                        if (!(e->pipe_skip & 1)) CK(launch_k((ppdl & 1) != 0, front_kernel, dim3(k == 0 ? 2 : 1, B), dim3(256), FRONT_SMEM, sF, a.x, a.xbs, a.xcs,
                                                              a.x_len, a.wsp + (int64_t)k * slot + ws.X, state, ss, e->w, 1, a.pos_rel, a.emb, PRE, k, K, k * HOP));
+                        if (k == 0) {                  // ... and every attn_out lane of block 0 (the gate's only reader) waits for it once
+                            cudaEvent_t gate_ev;
+                            if (int rc = record(&gate_ev, sF)) return rc;
+                            for (int ln = 0; ln < e->pipe_olanes; ++ln) CK(cudaStreamWaitEvent(sBo(0, ln), gate_ev, 0));
+                        }
                         if (int rc = edge(sF, st_a)) return rc;
                     } else {
                         CK(cudaStreamWaitEvent(st_a, out_done[b - 1][k], 0));
