@@ -482,12 +482,13 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
     if (fused_tail) {      // the frame as 13 row tiles: spectrum of the tile's bins, conv, and block 0's input projection
         CK(launch_k(false, front1_kernel, dim3(TAIL_TILES + 1, B), dim3(256), FRONT1_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w,
                     e->bw[0], GX, a.pos_rel, emb, PRE));
-    } else if (T > 1 && e->use_back_many) {      // many frames: one CTA walks a chunk of a stream's frames (one CTA per SM: 150 KB of filters)
+    } else if ((T > 1 || tc) && e->use_back_many) {      // many frames / streams: one CTA walks (stream, chunk) items (one CTA per SM: 150 KB of filters)
         const int per_stream = std::max(1, 148 / B);
         const int chunk = (T + per_stream - 1) / per_stream;
         const int n_chunks = (T + chunk - 1) / chunk;
-        CK(launch_k(false, front_many_kernel, dim3(n_chunks + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
-                    a.pos_rel, emb, PRE, chunk, n_chunks));
+        const int n_workers = std::min(148, B * n_chunks);
+        CK(launch_k(false, front_many_kernel, dim3(n_workers + B, 1), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
+                    a.pos_rel, emb, PRE, chunk, n_chunks, B, n_workers));
     } else {
         CK(launch_k(false, front_kernel, dim3(T + 1, B), dim3(256), FRONT_SMEM, st, x, xbs, xcs, x_len, X, state, ss, e->w, T,
                     a.pos_rel, emb, PRE, 0, 1, 0));
@@ -637,8 +638,8 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         if (tc && !tc_mid) {      // Q|K|V projections of all rows as one tensor-core GEMM (+ bias + PReLU per column)
             if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
         }
-        if (tc && (int64_t)B * T >= 296) {      // many frames: persistent form (LayerNorm parameters staged once per CTA)
-            CK(launch_k(pdl, qkv_many_kernel, dim3(296), dim3(QKV_THREADS), QKV_MANY_SMEM, st, (const float*)QKVRAW, Q, KALL, VALL, state, ss,
+        if (tc && (int64_t)B * T >= 148) {      // many frames: persistent form (LayerNorm parameters staged once per CTA, two CTAs per SM)
+            CK(launch_k(pdl, qkv_many_kernel, dim3((unsigned)std::min<int64_t>(296, (int64_t)B * T)), dim3(QKV_THREADS), QKV_MANY_SMEM, st, (const float*)QKVRAW, Q, KALL, VALL, state, ss,
                         b, W, T, B * T));
         } else {
             CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
@@ -668,14 +669,16 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         MARK("attn_out");
         if (int rc = do_tap()) return rc;
     }
-    if (T > 1 && e->use_back_many) {
-        // many frames: one cluster walks a contiguous chunk of a stream's frames (filters loaded once, rows staged once);
-        // as many clusters as stay resident together (3 CTAs of 72 KB per SM)
-        const int per_stream = std::max(1, (148 * 3 / BACK_CL) / B);
+    if ((T > 1 || tc) && e->use_back_many) {
+        // many frames (or many streams): one cluster walks (stream, chunk-of-frames) items -- filters loaded once per cluster, rows
+        // staged once; as many clusters as stay resident together (3 CTAs of 72 KB per SM)
+        const int max_cl = 148 * 3 / BACK_CL;
+        const int per_stream = std::max(1, max_cl / B);
         const int chunk = (T + per_stream - 1) / per_stream;
         const int n_chunks = (T + chunk - 1) / chunk;
-        CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_many_kernel, dim3(BACK_CL * n_chunks, B), dim3(256), BACK_MANY_SMEM, st, (const float*)X, y, ybs,
-                          ycs, y_len, state, ss, e->w, T, a.pos_rel, chunk));
+        const int n_cl = std::min(max_cl, B * n_chunks);
+        CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_many_kernel, dim3(BACK_CL * n_cl, 1), dim3(256), BACK_MANY_SMEM, st, (const float*)X, y, ybs,
+                          ycs, y_len, state, ss, e->w, T, a.pos_rel, chunk, n_chunks, B));
     } else {
         CK(launch_cluster(pdl, dim3(BACK_CL, 1, 1), back_kernel, dim3(BACK_CL * T, B), dim3(256), BACK_SMEM, st, (const float*)X, y, ybs, ycs, y_len, state, ss, e->w, T,
                     a.pos_rel, 0, 1, 0, (int64_t)0));

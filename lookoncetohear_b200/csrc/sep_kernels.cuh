@@ -205,19 +205,18 @@ front_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, 
 __global__ void __launch_bounds__(256)
 front_many_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstride, int x_len, float* __restrict__ X,
                   float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, const float* __restrict__ emb,
-                  float* __restrict__ spk_pre, int chunk, int n_chunks) {
+                  float* __restrict__ spk_pre, int chunk, int n_chunks, int n_streams, int n_workers) {
     extern __shared__ __align__(16) float wat_s[];     // [192][196]
     __shared__ __align__(16) float xs[NMIC][NFFT];      // the samples of the frame being transformed (>= 288 floats: gate CTA scratch)
     __shared__ float U[3][4][100];      // ring: frame g -> slot (g + 3) % 3; [ch][1 + f], zero-padded in f
     __shared__ __align__(8) unsigned long long wbar;
     griddep_launch();
-    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    if (c == n_chunks) {               // the extra CTA of this stream: speaker-gate memo
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x >= n_workers) {        // one more CTA per stream: speaker-gate memo
         griddep_wait();
-        spk_gate_cta(emb, spk_pre, state, sstride, w, b, &xs[0][0]);
+        spk_gate_cta(emb, spk_pre, state, sstride, w, (int)blockIdx.x - n_workers, &xs[0][0]);
         return;
     }
-    const int t0 = c * chunk, t1 = min(T, t0 + chunk);
     if (tid == 0) { mbar_init(&wbar, 1); mbar_fence_init(); }
     __syncthreads();
     if (tid == 0) { mbar_expect_tx(&wbar, (unsigned)FRONT_SMEM); tma_load_1d(wat_s, w.wat, (unsigned)FRONT_SMEM, &wbar); }
@@ -230,10 +229,15 @@ front_many_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstr
     griddep_wait();
     const StateHeader* hdr = reinterpret_cast<const StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
+    const int sbase = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
+    mbar_wait(&wbar, 0);
+    // one CTA walks (stream, chunk) items: frames [c*chunk, min(T, (c+1)*chunk)) of stream b
+    for (int item = blockIdx.x; item < n_streams * n_chunks; item += n_workers) {
+    const int b = item / n_chunks, c = item % n_chunks;
+    const int t0 = c * chunk, t1 = min(T, t0 + chunk);
     float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
     const float* cb = st + ST_CONV + par * (2 * 4 * NF);
     float* cb_next = st + ST_CONV + (par ^ 1) * (2 * 4 * NF);
-    const int sbase = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
     const float* xb = x + (int64_t)b * x_bstride;
     // samples of frame g: x[sbase + 128 g .. + 191] (zero outside the clip); thread tid fetches entries tid and tid + 256 of [2][192]
     auto fetch = [&](int g, float& a0, float& a1) {
@@ -262,7 +266,6 @@ front_many_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstr
         }
     };
     float n0, n1;
-    mbar_wait(&wbar, 0);
     // the two frames before the chunk: from the tails of the previous call (g < 0) or recomputed
     for (int g = t0 - 2; g < t0; ++g) {
         __syncthreads();
@@ -313,6 +316,8 @@ front_many_kernel(const float* __restrict__ x, int64_t x_bstride, int64_t x_cstr
                 cb_next[4 * NF + e] = U[(t + 3) % 3][e / NF][1 + e % NF];
             }
         }
+    }
+    __syncthreads();                               // the item's last conv is done before the next item refills the ring
     }
 }
 
@@ -1267,21 +1272,20 @@ constexpr size_t BACK_MANY_SMEM = (size_t)(4 * (BACK_FMAX + 2) * 64 + 2 * BACK_F
 
 __global__ void __launch_bounds__(256)
 back_many_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_bstride, int64_t y_cstride, int y_len,
-                 float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int chunk) {
+                 float* __restrict__ state, int64_t sstride, SepWeights w, int T, int pos_rel, int chunk, int n_chunks, int n_streams) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                                    // ring [4: frame g -> slot (g + 4) & 3][nf + 2 rows: f0-1 .. f1][64]
     float* Wf = Xs + 4 * (BACK_FMAX + 2) * 64;         // [2: re, im][nf][192] this CTA's synthesis filter rows
     float* R = Wf + 2 * BACK_FMAX * NFFT;              // [2: frame g -> g & 1][2 ears][194]  (own bins only)
-    float* wacc = R + 2 * NSRC * NROW;                 // [2: frame g & 1][2 ears][192] partial synthesis sums
+    float* wacc = R + 2 * NSRC * NROW;                 // [2: alternating per frame][2 ears][192] partial synthesis sums
     __shared__ __align__(8) unsigned long long fbar;   // filter
     __shared__ __align__(8) unsigned long long xbar[4];// one per ring slot
     const int part = (int)cluster.block_rank();
-    const int c = blockIdx.x / BACK_CL, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = blockIdx.x / BACK_CL, n_cl = gridDim.x / BACK_CL, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int f0 = back_f0(part), f1 = back_f0(part + 1), nf = f1 - f0;
     const int ld = nf + 2;
-    const int t0 = c * chunk, t1 = min(T, t0 + chunk);
     griddep_launch();
     if (tid == 0) {
         mbar_init(&fbar, 1);
@@ -1308,51 +1312,62 @@ back_many_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_b
     StateHeader* hdr = reinterpret_cast<StateHeader*>(state);
     const int par = (int)(hdr->ncalls & 1);
     const int soff = pos_rel ? (int)(hdr->pos - hdr->clip_base) * HOP : 0;
-    float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
-    const float* db = st + ST_DECONV + par * (2 * FC);
-    float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
-    const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
-    float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
     const int lo = max(f0 - 1, 0), hi = min(f1 + 1, NF);          // staged bins that exist: [lo, hi)
-    // frame g of this call: g >= 0 from X, g = -1, -2 from the deconv tails the previous call left
-    auto stage = [&](int g) {                                     // thread 0
-        const int slot = (g + 4) & 3;
-        const float* src = (g < 0) ? db + (2 + g) * FC : X + ((int64_t)b * T + g) * FC;
-        fence_proxy_async();
-        mbar_expect_tx(&xbar[slot], (hi - lo) * 64 * 4);
-        tma_load_1d(Xs + (slot * ld + (lo - (f0 - 1))) * 64, src + lo * 64, (hi - lo) * 64 * 4, &xbar[slot]);
-    };
-    const int gfirst = max(t0 - 3, -2);                           // first frame this cluster stages
-    auto slot_parity = [&](int g) { return (unsigned)(((g - gfirst) >> 2) & 1); };      // a slot's barrier completes once per 4 frames
-    // deconv of the own bins for frame g (needs frames g, g-1, g-2 in the ring) -> R[g & 1]
-    auto deconv = [&](int g) {
-        float* Rg = R + (g & 1) * NSRC * NROW;
-        for (int f = f0 + warp; f < f1; f += 8) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const float* xp = Xs + ((((g - i) + 4) & 3) * ld + (f + 2 - j - f0)) * 64;
-                    const float x0 = xp[lane], x1 = xp[lane + 32];
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        acc[o] = fmaf(wr[0][o * 9 + i * 3 + j], x0, acc[o]);
-                        acc[o] = fmaf(wr[1][o * 9 + i * 3 + j], x1, acc[o]);
-                    }
-                }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const float v = warp_sum(acc[o]);
-                if (lane == 0) Rg[(o >> 1) * NROW + (o & 1) * NF + f] = v + bd[o];
+    // ring-slot barriers: bit s of usebits = parity the NEXT staging into slot s completes; waitbits = parity to wait for the latest one
+    unsigned usebits = 0u, waitbits = 0u;
+    unsigned nframe = 0u;                               // frames this cluster has finished (selects the wacc buffer)
+    mbar_wait(&fbar, 0);
+    // one cluster walks (stream, chunk) items: frames [c*chunk, min(T, (c+1)*chunk)) of stream b
+    for (int item = cl; item < n_streams * n_chunks; item += n_cl) {
+        const int b = item / n_chunks, c = item % n_chunks;
+        const int t0 = c * chunk, t1 = min(T, t0 + chunk);
+        float* st = state + sizeof(StateHeader) / 4 + (int64_t)b * sstride;
+        const float* db = st + ST_DECONV + par * (2 * FC);
+        float* db_next = st + ST_DECONV + (par ^ 1) * (2 * FC);
+        const float* ib = st + ST_ISTFT + par * (NSRC * NROW);
+        float* ib_next = st + ST_ISTFT + (par ^ 1) * (NSRC * NROW);
+        // frame g of this call: g >= 0 from X, g = -1, -2 from the deconv tails the previous call left
+        auto stage = [&](int g) {                                     // bookkeeping by every thread, the copy by thread 0
+            const int slot = (g + 4) & 3;
+            waitbits = (waitbits & ~(1u << slot)) | (((usebits >> slot) & 1u) << slot);
+            usebits ^= 1u << slot;
+            if (tid == 0) {
+                const float* src = (g < 0) ? db + (2 + g) * FC : X + ((int64_t)b * T + g) * FC;
+                fence_proxy_async();
+                mbar_expect_tx(&xbar[slot], (hi - lo) * 64 * 4);
+                tma_load_1d(Xs + (slot * ld + (lo - (f0 - 1))) * 64, src + lo * 64, (hi - lo) * 64 * 4, &xbar[slot]);
             }
-        }
-    };
-    if (t0 < t1) {
-        // prologue: frames t0-3 .. t0 into the ring (those that exist: >= -2), then the spectrum of frame t0-1
-        if (tid == 0)
-            for (int g = gfirst; g <= t0; ++g) stage(g);
-        for (int g = gfirst; g < t0; ++g) mbar_wait(&xbar[(g + 4) & 3], slot_parity(g));
+        };
+        auto wait_frame = [&](int g) { const int slot = (g + 4) & 3; mbar_wait(&xbar[slot], (waitbits >> slot) & 1u); };
+        // deconv of the own bins for frame g (needs frames g, g-1, g-2 in the ring) -> R[g & 1]
+        auto deconv = [&](int g) {
+            float* Rg = R + (g & 1) * NSRC * NROW;
+            for (int f = f0 + warp; f < f1; f += 8) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float* xp = Xs + ((((g - i) + 4) & 3) * ld + (f + 2 - j - f0)) * 64;
+                        const float x0 = xp[lane], x1 = xp[lane + 32];
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            acc[o] = fmaf(wr[0][o * 9 + i * 3 + j], x0, acc[o]);
+                            acc[o] = fmaf(wr[1][o * 9 + i * 3 + j], x1, acc[o]);
+                        }
+                    }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float v = warp_sum(acc[o]);
+                    if (lane == 0) Rg[(o >> 1) * NROW + (o & 1) * NF + f] = v + bd[o];
+                }
+            }
+        };
+        // prologue of the item: frames t0-3 .. t0 into the ring (those that exist: >= -2), then the spectrum of frame t0-1
+        __syncthreads();                               // the previous item's readers of the ring and of R are done
+        const int gfirst = max(t0 - 3, -2);
+        for (int g = gfirst; g <= t0; ++g) stage(g);
+        for (int g = gfirst; g < t0; ++g) wait_frame(g);
         if (t0 == 0) {                                 // the previous call's last spectrum (own bins)
             for (int i = tid; i < NSRC * 2 * nf; i += 256) {
                 const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
@@ -1361,60 +1376,59 @@ back_many_kernel(const float* __restrict__ X, float* __restrict__ y, int64_t y_b
         } else {
             deconv(t0 - 1);
         }
-        mbar_wait(&fbar, 0);
-    }
-    for (int t = t0; t < t1; ++t) {
-        mbar_wait(&xbar[(t + 4) & 3], slot_parity(t));
-        __syncthreads();                               // frame t-1's readers of slot (t+1) & 3 = frame t-3's are done; R[(t-1)&1] complete
-        if (tid == 0 && t + 1 < t1) stage(t + 1);      // into the slot of frame t-3
-        deconv(t);
-        if (t == T - 1) {                              // next deconv tails: frames T-2, T-1 (own bins)
-            for (int i = tid; i < nf * 16; i += 256) {
-                const int r = i / 16, c4 = i % 16;
-                reinterpret_cast<float4*>(db_next + (f0 + r) * 64)[c4] =
-                    reinterpret_cast<const float4*>(Xs + ((((t - 1) + 4) & 3) * ld + 1 + r) * 64)[c4];
-                reinterpret_cast<float4*>(db_next + FC + (f0 + r) * 64)[c4] =
-                    reinterpret_cast<const float4*>(Xs + (((t + 4) & 3) * ld + 1 + r) * 64)[c4];
-            }
-        }
-        __syncthreads();                               // R[t & 1] (own bins) complete
-        float* wa = wacc + (t & 1) * NSRC * NFFT;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int item = tid + 256 * u;
-            if (item < NSRC * NFFT) {
-                const int ear = item / NFFT, n = item % NFFT;
-                const float* rr = R + ((((n < HOP) ? t : t - 1) & 1) * NSRC + ear) * NROW + f0;
-                float acc = 0.f;
-                for (int ri = 0; ri < 2; ++ri) {
-                    const float* wf = Wf + ri * nf * NFFT + n;
-                    const float* rv = rr + ri * NF;
-#pragma unroll 5
-                    for (int r = 0; r < nf; ++r) acc = fmaf(rv[r], wf[r * NFFT], acc);
+        for (int t = t0; t < t1; ++t, ++nframe) {
+            wait_frame(t);
+            __syncthreads();                           // frame t-1's readers of frame t-3's slot are done; R[(t-1)&1] complete
+            if (t + 1 < t1) stage(t + 1);              // into the slot of frame t-3
+            deconv(t);
+            if (t == T - 1) {                          // next deconv tails: frames T-2, T-1 (own bins)
+                for (int i = tid; i < nf * 16; i += 256) {
+                    const int r = i / 16, c4 = i % 16;
+                    reinterpret_cast<float4*>(db_next + (f0 + r) * 64)[c4] =
+                        reinterpret_cast<const float4*>(Xs + ((((t - 1) + 4) & 3) * ld + 1 + r) * 64)[c4];
+                    reinterpret_cast<float4*>(db_next + FC + (f0 + r) * 64)[c4] =
+                        reinterpret_cast<const float4*>(Xs + (((t + 4) & 3) * ld + 1 + r) * 64)[c4];
                 }
-                wa[item] = acc;
             }
-        }
-        if (t == T - 1)
-            for (int i = tid; i < NSRC * 2 * nf; i += 256) {
-                const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
-                ib_next[idx] = R[(t & 1) * NSRC * NROW + idx];
-            }
-        cluster.sync();                                // the four partial windows of frame t are complete and visible cluster-wide
-        if (part == 0) {                               // (wacc is double-buffered: the peers go on with frame t+1 meanwhile)
-            for (int i = tid; i < NSRC * HOP; i += 256) {
-                const int ear = i / HOP, n = i % HOP;
-                const int s = HOP * t + n + soff;
-                if (s < y_len) {
-                    float v = 0.f, tail = 0.f;
+            __syncthreads();                           // R[t & 1] (own bins) complete
+            float* wa = wacc + (nframe & 1u) * NSRC * NFFT;
 #pragma unroll
-                    for (int p = 0; p < BACK_CL; ++p) {
-                        const float* pw = cluster.map_shared_rank(wa, p);
-                        v += pw[ear * NFFT + n];
-                        if (n < LOOKAHEAD) tail += pw[ear * NFFT + HOP + n];
+            for (int u = 0; u < 2; ++u) {
+                const int it2 = tid + 256 * u;
+                if (it2 < NSRC * NFFT) {
+                    const int ear = it2 / NFFT, n = it2 % NFFT;
+                    const float* rr = R + ((((n < HOP) ? t : t - 1) & 1) * NSRC + ear) * NROW + f0;
+                    float acc = 0.f;
+                    for (int ri = 0; ri < 2; ++ri) {
+                        const float* wf = Wf + ri * nf * NFFT + n;
+                        const float* rv = rr + ri * NF;
+#pragma unroll 5
+                        for (int r = 0; r < nf; ++r) acc = fmaf(rv[r], wf[r * NFFT], acc);
                     }
-                    if (n < LOOKAHEAD) v += tail;               // overlap-add of the previous frame's tail
-                    y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s] = v;
+                    wa[it2] = acc;
+                }
+            }
+            if (t == T - 1)
+                for (int i = tid; i < NSRC * 2 * nf; i += 256) {
+                    const int idx = (i / (2 * nf)) * NROW + ((i / nf) & 1) * NF + f0 + i % nf;
+                    ib_next[idx] = R[(t & 1) * NSRC * NROW + idx];
+                }
+            cluster.sync();                            // the four partial windows of frame t are complete and visible cluster-wide
+            if (part == 0) {                           // (wacc is double-buffered: the peers go on with the next frame meanwhile)
+                for (int i = tid; i < NSRC * HOP; i += 256) {
+                    const int ear = i / HOP, n = i % HOP;
+                    const int s2 = HOP * t + n + soff;
+                    if (s2 < y_len) {
+                        float v = 0.f, tail = 0.f;
+#pragma unroll
+                        for (int p = 0; p < BACK_CL; ++p) {
+                            const float* pw = cluster.map_shared_rank(wa, p);
+                            v += pw[ear * NFFT + n];
+                            if (n < LOOKAHEAD) tail += pw[ear * NFFT + HOP + n];
+                        }
+                        if (n < LOOKAHEAD) v += tail;               // overlap-add of the previous frame's tail
+                        y[(int64_t)b * y_bstride + (int64_t)ear * y_cstride + s2] = v;
+                    }
                 }
             }
         }

@@ -360,8 +360,14 @@ def test_many_frame_front_and_back_kernels_are_bit_identical(model, dev):
     e = synth.embedding(3, seed0=592)
     xd, ed = x.to(dev), e.to(dev)
 
+    xm, _ = synth.mixture(40, 128 * 4, seed0=593)          # many streams, one hop per call: the same kernels walk (stream) items
+    em = synth.embedding(40, seed0=594)[:, 0].to(dev)
+    xm = xm.to(dev)
+
     def run_all():
         outs = [net(xd, ed).cpu(), net(xd[:1, :, :128 * 2], ed[:1]).cpu(), net(xd[:, :, :128 * 3 - 40], ed).cpu()]
+        outs.append(net.stream_dev(xm, em, chunks_per_call=1).cpu())
+        outs.append(net._last_stream_state.to_reference()["deconv_buf"].cpu())
         for cpc in (2, 3, 5):
             outs.append(net.stream_dev(xd[:, :, :128 * 41], ed[:, 0], chunks_per_call=cpc).cpu())
             ref = net._last_stream_state.to_reference()
