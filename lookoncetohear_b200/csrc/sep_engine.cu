@@ -109,6 +109,7 @@ struct SepEngine {
     bool mid_split_large = true;  // many streams: run the fused mid section as mid_a | mid_b | mid_c (2-4 CTAs per SM)
     bool use_mid = true;     // fused row-local mid-section for one-frame calls (option "fused_mid")
     int tcl_min_seqdirs = TCL_MIN_SEQDIRS;  // (sequence, direction) pairs from which the recurrence runs on the tensor cores (option "tc_lstm_min")
+    int tc_pdl = 7;              // programmatic dependent launch around the tensor-core GEMMs of many-row calls: bit 0 the many-stream mid section, bit 1 W_ih and the out projection + its LayerNorm kernel, bit 2 the persistent qkv kernel (256 streams: 0.847 -> 0.828 ms per hop-step; PDL on EVERY kernel of that chain was slower: 0.939; option "tc_pdl")
     bool use_back_many = true;   // calls of several frames: front_many_kernel / back_many_kernel (one CTA / cluster per chunk of frames) instead of one per frame (option "back_many")
     bool use_tail = true;    // one-hop calls of a few streams: mid + qkv + attention + attn_out (+ next W_ih) as ONE 16-CTA cluster kernel (option "fused_tail")
     bool use_pdl = true;     // programmatic dependent launch between the kernels of a chain (option "pdl")
@@ -516,7 +517,9 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             if (fused_tail) {
                 // front1_kernel (block 0) / the previous block's tail_kernel (its phase G) already wrote this block's input projection
             } else if (tc) {
+                e->cur_pdl = (e->tc_pdl & 2) != 0 && a.prof == nullptr;
                 if (int rc = tc_rows_gemm(e, b, PL_IH1, X, 64, 64, 512, W.ln1_g, W.ln1_b, W.b1, nullptr, nullptr, GX, 512, rows, st)) return rc;
+                e->cur_pdl = false;
             } else {
                 g.A = X; g.lda = 64; g.Wt = W.wih1_t; g.bias = W.b1; g.C = GX; g.ldc = 512;
                 g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; g.M = (int)rows; g.N = 512; g.K = 64;
@@ -530,6 +533,8 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             // many streams, one hop: the row-local middle of the block as four tensor-core GEMMs and the cell update.
             // The inter-LSTM step is ONE GEMM over the concatenated k = [LN(x) | h_prev] (h read in place from the
             // per-stream state records through a strided tensor map) against [W_ih | W_hh].
+            const bool mp = (e->tc_pdl & 1) != 0 && a.prof == nullptr;      // programmatic launches inside the section (experiment, option "tc_pdl")
+            e->cur_pdl = mp;
             if (int rc = tc_rows_gemm(e, b, PL_L1, Y, 128, 128, 64, nullptr, nullptr, W.bl1, nullptr, X, X, 64, rows, st)) return rc;
             {
                 umma::GemmDesc q;
@@ -543,14 +548,15 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
                 q.rows_per_seq = NF; q.nseq = B;
                 q.b = tc_planes(e, b, PL_CAT, 128); q.N = 256; q.K = 128; q.passes = e->tc_passes;
                 q.bias = W.b2; q.C = GX; q.ldc = 256; q.c_seq_stride = (int64_t)NF * 256;
-                q.pdl = false;
+                q.pdl = mp;
                 std::string why;
                 const cudaError_t ce = umma::launch(q, st, &why);
                 if (ce != cudaSuccess) return fail(3, std::string("umma_gemm (inter step): ") + cudaGetErrorString(ce) + " " + why);
             }
-            CK(launch_k(pdl, lstm_cell_rows_kernel, dim3((unsigned)((rows * 64 + 255) / 256)), dim3(256), 0, st, (const float*)GX, state, ss, b, Y, (int)rows));
+            CK(launch_k(pdl || mp, lstm_cell_rows_kernel, dim3((unsigned)((rows * 64 + 255) / 256)), dim3(256), 0, st, (const float*)GX, state, ss, b, Y, (int)rows));
             if (int rc = tc_rows_gemm(e, b, PL_L2, Y, 64, 64, 64, nullptr, nullptr, W.bl2, nullptr, X, X, 64, rows, st)) return rc;
             if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
+            e->cur_pdl = false;
             MARK("mid");
         } else if (fused_mid && mid_split_for_throughput(B) && e->mid_split_large) {
             float* GI = GX; float* HN = GX + rows * 256;         // the BiLSTM is done with GX
@@ -639,7 +645,7 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
             if (int rc = tc_rows_gemm(e, b, PL_QKV, X, 64, 64, NQKV, nullptr, nullptr, W.bqkv, W.slope_vec, nullptr, QKVRAW, NQKV, rows, st)) return rc;
         }
         if (tc && (int64_t)B * T >= 148) {      // many frames: persistent form (LayerNorm parameters staged once per CTA, two CTAs per SM)
-            CK(launch_k(pdl, qkv_many_kernel, dim3((unsigned)std::min<int64_t>(296, (int64_t)B * T)), dim3(QKV_THREADS), QKV_MANY_SMEM, st, (const float*)QKVRAW, Q, KALL, VALL, state, ss,
+            CK(launch_k(pdl || ((e->tc_pdl & 4) != 0 && a.prof == nullptr), qkv_many_kernel, dim3((unsigned)std::min<int64_t>(296, (int64_t)B * T)), dim3(QKV_THREADS), QKV_MANY_SMEM, st, (const float*)QKVRAW, Q, KALL, VALL, state, ss,
                         b, W, T, B * T));
         } else {
             CK(launch_k(pdl, qkv_kernel, dim3(T, B), dim3(QKV_THREADS), QKV_SMEM, st, (const float*)X,
@@ -659,8 +665,11 @@ static int enqueue_chain(SepEngine* e, const ChainArgs& a, cudaStream_t st) {
         }
         MARK("attn");
         if (tc) {      // Linear(64->64) + PReLU of all rows on the tensor cores, then LayerNorm(6208) + residual (+ gate) per frame
+            const bool p2 = (e->tc_pdl & 2) != 0 && a.prof == nullptr;
+            e->cur_pdl = p2;
             if (int rc = tc_rows_gemm(e, b, PL_P, Z, 64, 64, 64, nullptr, nullptr, W.bp, nullptr, nullptr, Y, 64, rows, st, W.slopes + 3)) return rc;
-            CK(launch_k(pdl, ln_frame_res_kernel, dim3(T, B), dim3(256), 0, st, (const float*)Y, X, (const float*)state, ss, W,
+            e->cur_pdl = false;
+            CK(launch_k(pdl || p2, ln_frame_res_kernel, dim3(T, B), dim3(256), 0, st, (const float*)Y, X, (const float*)state, ss, W,
                         (b == 0 && e->n_blocks > 1) ? 1 : 0, T));
         } else {
             CK(launch_k(pdl, attn_out_kernel, dim3(T, B), dim3(256), AOUT_SMEM, st, (const float*)Z, X, (const float*)state, ss, W,
@@ -1409,6 +1418,7 @@ int l2h_sep_set_option(void* handle, const char* name, int32_t value) {
     else if (n == "fused_mid") e->use_mid = value != 0;
     else if (n == "fused_tail") e->use_tail = value != 0;
     else if (n == "back_many") e->use_back_many = value != 0;
+    else if (n == "tc_pdl") e->tc_pdl = (int)value;
     else if (n == "tc_lstm_min") e->tcl_min_seqdirs = std::max(1, (int)value);
     else if (n == "mid_split_large") e->mid_split_large = value != 0;
     else if (n == "fold_mid_c") e->fold_mid_c = value != 0;
