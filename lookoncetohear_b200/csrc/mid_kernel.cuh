@@ -478,7 +478,8 @@ mid_c_kernel(const float* __restrict__ Hn, float* __restrict__ X, float* __restr
 }
 
 // The fused kernel without phase 6 (engine option "fold_mid_c": qkv_kernel projects Q/K/V itself, and the pipelined graph has
-// no mid_c).  Same text as mid_kernel up to X2.  NOT YET RUN ON HARDWARE; off by default.
+// no mid_c).  Same text as mid_kernel up to X2.  Off by default: measured slower in the pipeline (profiles/r02e_fold_mid_c_pipeline.jsonl);
+// covered by tests/test_sep_gpu.py::test_fold_mid_c_option.
 __global__ void __launch_bounds__(256)
 mid_noproj_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __restrict__ QKV, float* __restrict__ state,
            int64_t sstride, int blk, BlockWeights w, int n_streams) {
@@ -592,7 +593,7 @@ mid_noproj_kernel(const float* __restrict__ Y, float* __restrict__ X, float* __r
 
 // mid_b + the inter Linear (engine option "fold_mid_c", with qkv_kernel doing its own Q/K/V projection): the serial stage also
 // finishes X2 = X1 + h' W_l2 + b, so that no mid_c launch (and no graph edge for it) is left between it and qkv.
-// NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent); off by default.
+// Off by default (8.64 vs 7.27 us per hop, profiles/r02e_fold_mid_c_pipeline.jsonl); covered by tests/test_sep_gpu.py::test_fold_mid_c_option.
 constexpr size_t MID_B2_SMEM = (size_t)((MID_W5 - MID_W3B) + MID_A3 + (MID_W6 - MID_W5) + MID_A5) * sizeof(float);
 __global__ void __launch_bounds__(256)
 mid_b2_kernel(const float* __restrict__ GI, float* __restrict__ X, int64_t hop_stride, int n_hops, float* __restrict__ state,
