@@ -167,6 +167,13 @@ tail_kernel(const float* __restrict__ Y, float* X, float* __restrict__ state, in
         }
     }
     __syncthreads();
+    // the carried-state half of the inter-LSTM step (h_prev W_hh, old c): inputs of the PREVIOUS hop only -> before the dependency wait
+    float hv[8];
+    float2 cold = make_float2(0.f, 0.f);
+    if (has_tile) {
+        mbar_wait(&wbar, 0);
+        mid_h_product(S, sb + BK_H, sb + BK_C, r0, nr, tid, hv, cold);
+    }
     griddep_wait();
     const long long pos = reinterpret_cast<const StateHeader*>(state)->pos + frame_k;
     trace_.mark(0);
@@ -178,9 +185,8 @@ tail_kernel(const float* __restrict__ Y, float* X, float* __restrict__ state, in
             if (ok0) gate0 = st[ST_GATE + (r0 + rp) * 64 + n_o];
             if (ok1) gate1 = st[ST_GATE + (r0 + rp + 4) * 64 + n_o];
         }
-        mbar_wait(&wbar, 0);
         const int64_t row0 = (int64_t)b * NF + r0;
-        mid_tile(S, Y + row0 * 128, X + row0 * 64, x2s, Ps, sb + BK_H, sb + BK_C, r0, nr, vs, tid);
+        mid_tile<true>(S, Y + row0 * 128, X + row0 * 64, x2s, Ps, sb + BK_H, sb + BK_C, r0, nr, vs, tid, hv, cold);
         __syncthreads();
         if (tid == 0) {                    // the mid weights are dead: W_p (and the next block's W_ih) take their place
             fence_proxy_async();

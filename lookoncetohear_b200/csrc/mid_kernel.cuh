@@ -134,8 +134,31 @@ __device__ __forceinline__ void mid_stage_vecs(float* vs, const BlockWeights& w,
 // global for mid_kernel, the caller's shared memory for tail_kernel (hop_kernels.cuh); Xin may alias X2out.
 // hst/cst: the stream's carried (h, c) of this block, [97][64].  vs: the vectors staged by mid_stage_vecs (visible to all
 // threads after the first barrier in here).  The caller has waited for the weights.
+// The carried-state half of the inter-LSTM step of a tile, h_prev W_hh (lane (jp, kq = row) keeps gates of hidden units 2jp, 2jp+1 of
+// row kq: hv[0..7]) and the tile's old cell state.  It reads only what the PREVIOUS hop left, so tail_kernel runs it before the
+// dependency wait, under the recurrence that is still going.  Needs W_hh (MID_W3B) in shared memory; ends with a barrier pending
+// (the caller's next barrier separates it from the next writer of A3h).
+__device__ __forceinline__ void mid_h_product(const MidSmem& S, const float* hst, const float* cst, int r0, int nr, int tid,
+                                              float (&hv)[8], float2& cold) {
+    if (tid < 128) {
+        const int r = tid >> 4, k4 = tid & 15;
+        const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        S.A3h[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; S.A3h[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
+        S.A3h[mid_aidx(M3_KS, k4 * 4 + 2, r)] = v.z; S.A3h[mid_aidx(M3_KS, k4 * 4 + 3, r)] = v.w;
+    }
+    cold = ((tid & 7) < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + (tid & 7)) * 64 + (tid >> 3) * 2) : make_float2(0.f, 0.f);
+    __syncthreads();
+    float v[MID_RT * M3_C];
+    mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(S.Wp + MID_W3B, S.A3h, tid >> 3, tid & 7, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hv[i] = v[i];
+}
+
+// PRE_H: the h W_hh product and the old cell state come from mid_h_product (hv_in, cold_in) instead of being computed here.
+template <bool PRE_H = false>
 __device__ __forceinline__ void mid_tile(const MidSmem& S, const float* Yrows, const float* Xin, float* X2out, float* Pout,
-                                         float* hst, float* cst, int r0, int nr, const float* vs, int tid) {
+                                         float* hst, float* cst, int r0, int nr, const float* vs, int tid,
+                                         const float* hv_in = nullptr, float2 cold_in = make_float2(0.f, 0.f)) {
     float* Wp = S.Wp; float* A1 = S.A1; float* A3 = S.A3; float* A3h = S.A3h; float* A5 = S.A5; float* A6 = S.A6; float* x1s = S.x1s;
     // ---- tile loads: Y -> A1, h -> A3h ------------------------------------------------------------
     {
@@ -144,7 +167,7 @@ __device__ __forceinline__ void mid_tile(const MidSmem& S, const float* Yrows, c
         A1[mid_aidx(M1_KS, k4 * 4 + 0, r)] = v.x; A1[mid_aidx(M1_KS, k4 * 4 + 1, r)] = v.y;
         A1[mid_aidx(M1_KS, k4 * 4 + 2, r)] = v.z; A1[mid_aidx(M1_KS, k4 * 4 + 3, r)] = v.w;
     }
-    if (tid < 128) {
+    if (!PRE_H && tid < 128) {
         const int r = tid >> 4, k4 = tid & 15;
         const float4 v = (r < nr) ? *reinterpret_cast<const float4*>(hst + (r0 + r) * 64 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         A3h[mid_aidx(M3_KS, k4 * 4 + 0, r)] = v.x; A3h[mid_aidx(M3_KS, k4 * 4 + 1, r)] = v.y;
@@ -153,7 +176,8 @@ __device__ __forceinline__ void mid_tile(const MidSmem& S, const float* Yrows, c
     // the two other chain inputs of this thread, requested now: the residual of phase 1 and the cell state of phase 4
     const int r1 = (tid & 15) >> 1, n1 = (tid >> 4) * 4 + (tid & 1) * 2;
     const float2 xo = (r1 < nr) ? *reinterpret_cast<const float2*>(Xin + (int64_t)r1 * 64 + n1) : make_float2(0.f, 0.f);
-    const float2 cold = ((tid & 7) < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + (tid & 7)) * 64 + (tid >> 3) * 2) : make_float2(0.f, 0.f);
+    float2 cold = cold_in;
+    if (!PRE_H) cold = ((tid & 7) < nr) ? *reinterpret_cast<const float2*>(cst + (r0 + (tid & 7)) * 64 + (tid >> 3) * 2) : make_float2(0.f, 0.f);
     __syncthreads();
     // ---- phase 1: X1 = X + Y W1 + b ;  lane (cg, kq) finishes row kq/2, columns cg*4 + (kq&1)*2 + {0,1}
     float2 x1v;
@@ -182,7 +206,12 @@ __device__ __forceinline__ void mid_tile(const MidSmem& S, const float* Yrows, c
         float u[MID_RT * M3_C], v[MID_RT * M3_C];
         const int jp = tid >> 3, r = tid & 7;
         mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3A, A3, jp, r, u);
-        mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3B, A3h, jp, r, v);
+        if (PRE_H) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = hv_in[i];
+        } else {
+            mid_mm<M3_C, M3_KQ, M3_KS, M3_N>(Wp + MID_W3B, A3h, jp, r, v);
+        }
         const float4 ba = *reinterpret_cast<const float4*>(vs + MV_B2 + jp * 8);
         const float4 bb = *reinterpret_cast<const float4*>(vs + MV_B2 + jp * 8 + 4);
         const float4 ga = make_float4(u[0] + ba.x, u[1] + ba.y, u[2] + ba.z, u[3] + ba.w);
