@@ -248,10 +248,14 @@ tail_kernel(const float* __restrict__ Y, float* X, float* __restrict__ state, in
             kv[rr][u] = (r < na_old && i < QK_LD / 4) ? __ldcg(kr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    float4 vpre[7];                                         // value rows 0..6 of this CTA's share, column tid
+    float4 vpre[7], vpre_b[7];                              // value rows 0..6 of this CTA's share: column tid and (threads < 132) tid + 256
+    const bool has_b = tid + 256 < V_DIM / 4;
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
-        vpre[j] = __ldcg(reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % RING) * V_DIM) + tid);
+    for (int j = 0; j < 7; ++j) {
+        const float4* vr = reinterpret_cast<const float4*>(vb + (int64_t)((first + j) % RING) * V_DIM);
+        vpre[j] = __ldcg(vr + tid);
+        vpre_b[j] = has_b ? __ldcg(vr + tid + 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid < 12) {
         const int d = ((tid >> 2) == 2) ? VD : QE;
         float mp[TAIL_TILES], m2[TAIL_TILES];
@@ -344,47 +348,35 @@ tail_kernel(const float* __restrict__ Y, float* X, float* __restrict__ state, in
             if (lane < na) sc[lane] = e0;
             if (lane == 0) { ml[0] = mx; ml[1] = lsum; }
         }
-        // rows 7 .. na-1 of column tid, and (threads < 132) the second column tid + 256
-        float4 v2[6];
+        // rows 7 .. na-1 of both columns in ONE batch of loads (they contain the row written during this launch)
+        float4 v2[6], v2b[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j)
-            v2[j] = (7 + j < na) ? __ldcg(reinterpret_cast<const float4*>(vb + (int64_t)((first + 7 + j) % RING) * V_DIM) + tid)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 6; ++j) {
+            const float4* vr = reinterpret_cast<const float4*>(vb + (int64_t)((first + 7 + j) % RING) * V_DIM);
+            v2[j] = (7 + j < na) ? __ldcg(vr + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v2b[j] = (has_b && 7 + j < na) ? __ldcg(vr + tid + 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncthreads();
         {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 const float p = sc[j];                     // na >= 12 > 7
                 acc.x = fmaf(p, vpre[j].x, acc.x); acc.y = fmaf(p, vpre[j].y, acc.y);
                 acc.z = fmaf(p, vpre[j].z, acc.z); acc.w = fmaf(p, vpre[j].w, acc.w);
+                accb.x = fmaf(p, vpre_b[j].x, accb.x); accb.y = fmaf(p, vpre_b[j].y, accb.y);
+                accb.z = fmaf(p, vpre_b[j].z, accb.z); accb.w = fmaf(p, vpre_b[j].w, accb.w);
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 const float p = (7 + j < na) ? sc[7 + j] : 0.f;
                 acc.x = fmaf(p, v2[j].x, acc.x); acc.y = fmaf(p, v2[j].y, acc.y);
                 acc.z = fmaf(p, v2[j].z, acc.z); acc.w = fmaf(p, v2[j].w, acc.w);
+                accb.x = fmaf(p, v2b[j].x, accb.x); accb.y = fmaf(p, v2b[j].y, accb.y);
+                accb.z = fmaf(p, v2b[j].z, accb.z); accb.w = fmaf(p, v2b[j].w, accb.w);
             }
             reinterpret_cast<float4*>(os)[tid] = acc;
-        }
-        if (tid + 256 < V_DIM / 4) {
-            const int c4 = tid + 256;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int jb = 0; jb < 14; jb += 7) {
-                float4 v[7];
-#pragma unroll
-                for (int j = 0; j < 7; ++j)
-                    v[j] = (jb + j < na) ? __ldcg(reinterpret_cast<const float4*>(vb + (int64_t)((first + jb + j) % RING) * V_DIM) + c4)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const float p = (jb + j < na) ? sc[jb + j] : 0.f;
-                    acc.x = fmaf(p, v[j].x, acc.x); acc.y = fmaf(p, v[j].y, acc.y);
-                    acc.z = fmaf(p, v[j].z, acc.z); acc.w = fmaf(p, v[j].w, acc.w);
-                }
-            }
-            reinterpret_cast<float4*>(os)[c4] = acc;
+            if (has_b) reinterpret_cast<float4*>(os)[tid + 256] = accb;
         }
     }
     trace_.mark(6);
