@@ -232,6 +232,7 @@ class Net(nn.Module):
         d = dict(self.__dict__)
         d["_handle"], d["_ws"], d["_dirty"] = None, None, True
         d.pop("_host_stage", None)
+        d.pop("_predict_stage", None)
         d.pop("_last_stream_state", None)
         d["_cfg"] = bytes(self._cfg)
         return d
@@ -455,6 +456,42 @@ class Net(nn.Module):
                 ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         self._last_stream_state = state
         return yh[..., :n] if out is not None else yh[..., :n].clone()
+
+    def predict_host(self, x_host, embed_dev, state, out=None):
+        """One streaming call with HOST buffers, natively (l2h_sep_stream_host with one call): x_host [B,M,128*T+64] PINNED (the
+        chunk plus the 64 look-ahead samples, as predict(..., pad=False) takes it) is copied host->device, the chain runs, the
+        128*T new samples per ear are copied back into `out` ([B,S,128*T] pinned; allocated once if None) and the stream is
+        synchronised -- the copies, the launch and the wait are one C call instead of four Python-level ops.  Returns (out, state)."""
+        dev = embed_dev.device
+        self._require_cuda(embed_dev)
+        self._sync_weights(dev)
+        hop, la = self.stft_chunk_size, self.stft_pad_size
+        Bsz, _, n = x_host.shape
+        if (n - la) % hop != 0 or n < hop + la:
+            raise ValueError(f"predict_host needs {hop}*T+{la} samples, got {n}")
+        frames = (n - la) // hop
+        if not (x_host.is_pinned() and x_host.is_contiguous() and x_host.dtype == torch.float32):
+            raise ValueError("x_host must be a contiguous pinned float32 tensor")
+        if not isinstance(state, SepState):
+            raise TypeError("state must come from Net.init_buffers()")
+        key = (Bsz, frames, str(dev))
+        cache = getattr(self, "_predict_stage", None)
+        if cache is None or cache[0] != key:
+            cache = (key, torch.empty(Bsz, self.num_src, hop * frames, dtype=torch.float32).pin_memory(),
+                     torch.empty(Bsz, self.num_ch, n, dtype=torch.float32, device=dev),
+                     torch.empty(Bsz, self.num_src, hop * frames, dtype=torch.float32, device=dev),
+                     self._stream_workspace(dev, Bsz, frames)[0])
+            self._predict_stage = cache
+        _, yh_c, xs, ys, ws = cache
+        emb = embed_dev if (embed_dev.dtype == torch.float32 and embed_dev.is_contiguous()) else embed_dev.to(torch.float32).contiguous()
+        yh = out if out is not None else yh_c
+        if not yh.is_pinned() or not yh.is_contiguous() or tuple(yh.shape) != (Bsz, self.num_src, hop * frames):
+            raise ValueError("out must be a contiguous pinned [B, S, 128*T] float32 tensor")
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().l2h_sep_stream_host(
+                self._engine(), x_host.data_ptr(), n, emb.data_ptr(), state.buf.data_ptr(), yh.data_ptr(), hop * frames, Bsz, 1,
+                frames, xs.data_ptr(), ys.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return yh, state
 
     # ---- debugging aid for the parity tests ------------------------------------------------------
     def forward_with_taps(self, x, embeds):

@@ -384,6 +384,25 @@ def test_many_frame_front_and_back_kernels_are_bit_identical(model, dev):
         assert torch.equal(u, v)
 
 
+def test_predict_host_equals_predict(model, dev):
+    """Net.predict_host (pinned chunk in, pinned samples out, one C call: H2D, chain, D2H, sync) == Net.predict on device tensors."""
+    net, _ = model
+    x, _ = synth.mixture(2, 128 * 9, seed0=691)
+    e = synth.embedding(2, seed0=692)[:, 0].to(dev)
+    xp = F.pad(x, (0, 64))
+    st_a, st_b = net.init_buffers(2, dev), net.init_buffers(2, dev)
+    chunk = torch.empty(2, 2, 192).pin_memory()
+    out = torch.empty(2, 2, 128).pin_memory()
+    with torch.no_grad():
+        for i in range(9):
+            chunk.copy_(xp[..., 128 * i:128 * i + 192])
+            ya, _ = net.predict_host(chunk, e, st_a, out=out)
+            yb, _ = net.predict(xp[..., 128 * i:128 * i + 192].to(dev), e, st_b, pad=False)
+            assert torch.equal(ya, yb.cpu())
+    with pytest.raises(ValueError):
+        net.predict_host(torch.empty(2, 2, 200).pin_memory(), e, st_a)
+
+
 def test_init_buffers_in_place(model, dev):
     """init_buffers(out=state) re-initialises a state at its address (the engine's graphs are keyed on it): same pointer,
     header back to zero, and the stream that follows equals one on a new state."""
