@@ -418,7 +418,7 @@ static int embed_forward_impl(EmbedEngine* e, const float* x, float* out, int B,
             g.C = O; g.ldc = VDIM; g.c_seq_stride = (int64_t)Tp * VDIM;
             CKU(umma::launch(g, st, &_why));
         }
-        eattn_out_kernel<<<dim3(T, B), 256, EAOUT_SMEM, st>>>(O, X, W, T, Tp);
+        eattn_out_kernel<<<dim3((unsigned)std::min<int64_t>((int64_t)T * B, 148 * 4)), 256, EAOUT_SMEM, st>>>(O, X, W, T, Tp, T * B);
         CK(cudaGetLastError());
     }
     // ---- head: Linear(4160 -> 256) over rows (b,t) [features f*64+c], LN, mean over T -----------
