@@ -157,3 +157,17 @@ def test_cpp_host_example_builds(lib, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
         assert r.returncode != 0 and "l2h_sep_commit_weights" in r.stderr
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """l2h_sep_set_option takes its switches by name: every name the engine accepts must appear in the header's description of
+    the call (and no environment variable may select a code path: the only getenv allowed in csrc/ would be none)."""
+    src = open(os.path.join(ROOT, "lookoncetohear_b200", "csrc", "sep_engine.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "lookonce_b200.h")).read()
+    names = sorted(set(re.findall(r'n == "([a-z_0-9]+)"', src)))
+    assert len(names) >= 20
+    for n in names:
+        assert f'"{n}"' in hdr, f'option "{n}" is accepted by l2h_sep_set_option but not documented in include/lookonce_b200.h'
+    csrc = os.path.join(ROOT, "lookoncetohear_b200", "csrc")
+    for fn in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, fn)).read(), f"{fn}: environment switches are not part of the interface"
